@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — edges·featdim/s of the fused 1-hop + 2-hop aggregation round (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (N > 1: one rank per GPU, rows sharded)
+
+A "step" is one fused round  Y[:, 0:d] = A1·X, Y[:, d:2d] = A2·X  over the workload named in `config.workload`
+(north-star target: uniform random graph |V|=10 000 per GPU, |E|=200 000 per GPU, d=128, fp32, explicit fp32
+adjacency values).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_PER_GPU = 10_000
+E_PER_GPU = 200_000
+FEAT = 128
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_rows, n_cols, nnz, d, explicit_vals=True):
+    """every distinct byte once.  rowptr is int64 here (8 B/row instead of the survey's 4)."""
+    return 2 * (n_rows + 1) * 8 + nnz * (4 + (4 if explicit_vals else 0)) + n_cols * d * 4 + 2 * n_rows * d * 4
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(n, n_edges, seed):
+    from h2gcn_b200.utils import synth
+    return synth.uniform_graph(n, n_edges, seed=seed)
+
+
+def cpu_baseline(hops_host, x, budget_s=10.0, min_rounds=3):
+    """Oracle C restatement (OpenMP over rows, every host thread) on full rounds of the SAME workload."""
+    from oracle import cbind  # the one place bench.py may run oracle/ (cpu_baseline / --impl reference)
+    (rp1, c1, v1), (rp2, c2, v2) = hops_host
+    n, d = x.shape
+    y = np.empty((n, 2 * d), dtype=np.float32)
+    cbind.fused_round(rp1, c1, v1, rp2, c2, v2, x, y)  # warm-up
+    rounds, t0 = 0, time.perf_counter()
+    while rounds < min_rounds or time.perf_counter() - t0 < budget_s:
+        cbind.fused_round(rp1, c1, v1, rp2, c2, v2, x, y)
+        rounds += 1
+    dt = time.perf_counter() - t0
+    nnz = len(c1) + len(c2)
+    return {"value": nnz * d * rounds / dt, "unit": "edges*featdim/s", "cores": cbind.max_threads(), "kind": "port",
+            "sample": f"{rounds} full fused rounds of the same workload in {dt:.1f} s (C restatement of the TF-CPU "
+                      f"functor, OpenMP over rows; TensorFlow is not installable here)", "ms_per_round": 1e3 * dt / rounds}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port — the reference is TensorFlow, which this image lacks)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cbind
+    from oracle import h2gcn_oracle as O
+    adj = build_workload(N_PER_GPU, E_PER_GPU, seed=0)
+    rp2, col2 = cbind.hop2_csr(adj.indptr, adj.indices)
+    import scipy.sparse as sp
+    p2 = sp.csr_matrix((np.ones(len(col2), dtype=np.float32), col2, rp2), shape=adj.shape)
+    a1 = O.sym_normalize(adj)[0]
+    a2 = O.sym_normalize(p2)[0]
+    hops = [(a1.indptr.astype(np.int64), a1.indices.astype(np.int32), a1.data.astype(np.float32)),
+            (a2.indptr.astype(np.int64), a2.indices.astype(np.int32), a2.data.astype(np.float32))]
+    from h2gcn_b200.utils import synth
+    x = synth.features(N_PER_GPU, FEAT, 0)
+    (rp1, c1, v1), (rpb, c2, v2) = hops
+    y = np.empty((N_PER_GPU, 2 * FEAT), dtype=np.float32)
+    for _ in range(max(1, args.warmup)):
+        cbind.fused_round(rp1, c1, v1, rpb, c2, v2, x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cbind.fused_round(rp1, c1, v1, rpb, c2, v2, x, y)
+    dt = time.perf_counter() - t0
+    nnz = len(c1) + len(c2)
+    val = nnz * FEAT * args.steps / dt
+    line = {"impl": "reference", "metric": "edges*featdim/sec on fused 2-hop SpMM", "value": val,
+            "unit": "edges*featdim/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"uniform random graph |V|={N_PER_GPU} |E|={E_PER_GPU} d={FEAT} fp32, seed 0",
+                       "nnz1": len(c1), "nnz2": len(c2), "note": "runs once on rank 0 (CPU), independent of --gpus"},
+            "cpu_baseline": {"value": val, "unit": "edges*featdim/s", "cores": cbind.max_threads(), "kind": "port",
+                             "sample": f"{args.steps} full fused rounds; C restatement of tf.sparse.sparse_dense_matmul "
+                                       "(TF-CPU functor order) with OpenMP over rows — TensorFlow itself is absent"},
+            "e2e": {"value": val, "unit": "edges*featdim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--factored", action="store_true", help="index-only CSR (val = dinv_i*dinv_j rebuilt in-kernel)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from h2gcn_b200 import _cabi
+    from h2gcn_b200.parallel import ShardedGraph
+    from h2gcn_b200.utils import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 through torchrun)"
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+
+    # ---- workload (untimed set-up: graph, GPU adjacency-power precompute, plan) ------------------------------------
+    n = N_PER_GPU * world
+    adj = build_workload(n, E_PER_GPU * world, seed=0)
+    t0 = time.perf_counter()
+    g = ShardedGraph(adj, rank, world, dev, factored=args.factored)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t0
+    d = FEAT
+    x_full = synth.features(n, d, 0)
+    x_local = torch.from_numpy(x_full[g.row_begin:g.row_end]).to(dev)
+    y = torch.empty(g.n_local, 2 * d, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step():
+        g.round(x_local, y, [0, d])
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps -----
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _cabi.launch_count()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.finish()
+    if world > 1:
+        dist.barrier()
+    times = np.array([a.elapsed_time(b) for a, b in ev])  # ms
+    total_ms = float(times.sum())
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+        nnz_t = torch.tensor([g.nnz_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(nnz_t)
+        nnz_total = int(nnz_t.item())
+    else:
+        nnz_total = g.nnz_local
+    ms_per_step = total_ms / args.steps
+    value = nnz_total * d / (ms_per_step * 1e-3)
+
+    # ---- e2e: the host-buffer C-ABI call (X host->device, round, Y device->host inside the timed region) -------------
+    e2e = None
+    if world == 1:
+        from h2gcn_b200.ops import HostGraph
+        hg = HostGraph(g.hops_host(), g.n_local, n, d_max=d)
+        xh = torch.from_numpy(x_full).pin_memory()
+        yh = torch.empty(g.n_local, 2 * d).pin_memory()
+        for _ in range(3):
+            hg.round(xh, yh)
+        k_e2e = min(args.steps, 50)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            flush.zero_()
+            hg.round(xh, yh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": nnz_total * d * k_e2e / dt, "unit": "edges*featdim/s", "h2d_bytes_per_step": n * d * 4,
+               "d2h_bytes_per_step": g.n_local * 2 * d * 4, "ms_per_step": 1e3 * dt / k_e2e, "steps": k_e2e,
+               "api": "h2_graph_round_host (adjacency resident, X in / Y out through pinned host buffers, sync per call)"}
+        assert float((yh.to(dev) - y).abs().max()) == 0.0, "host-buffer path and device path disagree"
+        hg.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    balg = algorithmic_bytes(g.n_local, n, g.nnz_local, d, explicit_vals=not args.factored)
+    kern_ms = float(times.mean())
+    achieved = balg / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("fused_round_dram_bytes_per_launch")
+    line = {
+        "metric": "edges*featdim/sec on fused 2-hop SpMM", "value": value, "unit": "edges*featdim/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"uniform random graph |V|={n} |E|={E_PER_GPU * world} d={d} fp32 "
+                               f"({'factored dinv' if args.factored else 'explicit fp32'} adjacency values), seed 0, "
+                               f"rows sharded over {world} GPU(s)",
+                   "n_vertices": n, "nnz1": g.nnz1_global, "nnz2_local": g.nnz2_local, "nnz_local": g.nnz_local,
+                   "nnz_total": nnz_total, "max_row_nnz": g.max_row_nnz, "kernel": g.kernel_name,
+                   "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write); each step timed by its own CUDA "
+                         "event pair, ms_per_step = sum/K (max over ranks)",
+                   "precompute_s": t_pre, "ms_per_step_min": float(times.min()), "ms_per_step_median": float(np.median(times)),
+                   "wall_s_timed_region": wall},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": balg,
+                     "kernel_ms": kern_ms, "note": "compulsory bytes (SURVEY §8d) / mean launch time of the fused round "
+                                                    "kernel on rank 0; one launch per step"},
+        "clocks": clocks, "gpu_launches": int(launches),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(g.hops_host(), x_full)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

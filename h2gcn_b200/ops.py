@@ -1,0 +1,299 @@
+"""Thin Python wrappers over the C-ABI (include/h2gcn_b200.h).  torch tensors are device buffers only.
+
+Everything here runs on the GPU through libh2gcn_b200.so; there is no CPU path (see _cabi.lib()).
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from ._cabi import HopDesc, check, lib, ptr, require_cuda, stream_ptr
+
+
+def _i64(t):
+    return t if t.dtype == torch.int64 else t.to(torch.int64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# device CSR container (what the reference carries around as a tf.SparseTensor, _dataset.py:528-535)
+# ------------------------------------------------------------------------------------------------------------------
+class SparseTensor:
+    """Row-major-sorted sparse matrix on the device: CSR (rowptr int64, col int32, values fp32).
+
+    Mirrors the attributes the reference reads from tf.SparseTensor (`indices`, `values`, `dense_shape`, `shape`);
+    `indices` ([nnz, 2] int64, row-major order = tf.sparse.reorder order) is materialised lazily.
+    `row_begin` is the global index of local row 0 when the rows are a shard (multi-GPU), else 0.
+    """
+
+    def __init__(self, rowptr, col, values, dense_shape, row_begin=0, dinv=None):
+        require_cuda(rowptr, col, values)
+        self.rowptr = _i64(rowptr).contiguous()
+        self.col = col.to(torch.int32).contiguous()
+        self.values = None if values is None else values.to(torch.float32).contiguous()
+        self.dense_shape = tuple(int(x) for x in dense_shape)
+        self.row_begin = int(row_begin)
+        self.dinv = dinv  # fp32 [n_cols] when the values factor as dinv[i]*dinv[j] (sym-normalised binary pattern)
+        self._indices = None
+
+    @property
+    def shape(self):
+        return self.dense_shape
+
+    @property
+    def n_rows(self):
+        return self.rowptr.numel() - 1
+
+    @property
+    def nnz(self):
+        return int(self.col.numel())
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    @property
+    def indices(self):
+        if self._indices is None:
+            counts = self.rowptr[1:] - self.rowptr[:-1]
+            rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device) + self.row_begin, counts)
+            self._indices = torch.stack([rows, self.col.to(torch.int64)], dim=1)
+        return self._indices
+
+    @classmethod
+    def from_scipy(cls, m, device="cuda", dtype=torch.float32):
+        """Host scipy matrix -> canonical device CSR (sorted, duplicates summed) — sparse2Tensor, _dataset.py:528-535."""
+        import numpy as np
+        import scipy.sparse as sp
+        m = sp.csr_matrix(m)
+        m.sum_duplicates()
+        m.sort_indices()
+        dev = torch.device(device)
+        return cls(torch.from_numpy(m.indptr.astype(np.int64)).to(dev), torch.from_numpy(m.indices.astype(np.int32)).to(dev),
+                   torch.from_numpy(m.data.astype(np.float32)).to(dev), m.shape)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.values.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.n_rows, self.dense_shape[1]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# precompute
+# ------------------------------------------------------------------------------------------------------------------
+def exclusive_scan(counts, stream=None):
+    """int64 counts[n] -> rowptr[n+1]."""
+    require_cuda(counts)
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    ws_bytes = lib().h2_scan_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=counts.device)
+    check(lib().h2_exclusive_scan_i64(n, ptr(counts), ptr(out), ptr(ws), ws_bytes, stream_ptr(stream)))
+    return out
+
+
+def remove_eye(rowptr, col, val=None, stream=None):
+    """TransformSPAdj.removeEye (_dataset.py:132-136) on a sorted CSR: drop diagonal entries.
+    Returns (rowptr, col) or (rowptr, col, val) when values are given."""
+    require_cuda(rowptr, col, val)
+    n = rowptr.numel() - 1
+    rowptr = _i64(rowptr).contiguous()
+    col = col.to(torch.int32).contiguous()
+    counts = torch.empty(n, dtype=torch.int64, device=rowptr.device)
+    s = stream_ptr(stream)
+    check(lib().h2_remove_eye_count(n, ptr(rowptr), ptr(col), ptr(counts), s))
+    rp = exclusive_scan(counts, stream)
+    nnz = int(rp[-1].item()) if n else 0
+    out = torch.empty(nnz, dtype=torch.int32, device=rowptr.device)
+    vout = None if val is None else torch.empty(nnz, dtype=torch.float32, device=rowptr.device)
+    if val is not None:
+        val = val.to(torch.float32).contiguous()
+    check(lib().h2_remove_eye_fill(n, ptr(rowptr), ptr(col), ptr(val), ptr(rp), ptr(out), ptr(vout), s))
+    return (rp, out) if val is None else (rp, out, vout)
+
+
+def hop2_pattern(rowptr, col, row_begin=0, row_end=None, stream=None):
+    """Exact-distance-2 pattern (nhoodSplit(adj, 2)[2], _dataset.py:138-158) of a self-loop-free sorted CSR.
+    Returns (rowptr2 int64 [rows+1], col2 int32) for rows [row_begin, row_end); one host sync (count -> alloc -> fill)."""
+    require_cuda(rowptr, col)
+    n = rowptr.numel() - 1
+    row_end = n if row_end is None else row_end
+    rowptr = _i64(rowptr).contiguous()
+    col = col.to(torch.int32).contiguous()
+    rows = row_end - row_begin
+    counts = torch.empty(rows, dtype=torch.int64, device=rowptr.device)
+    s = stream_ptr(stream)
+    check(lib().h2_hop2_count(n, ptr(rowptr), ptr(col), row_begin, row_end, ptr(counts), s))
+    rp2 = exclusive_scan(counts, stream)
+    nnz2 = int(rp2[-1].item()) if rows else 0
+    col2 = torch.empty(nnz2, dtype=torch.int32, device=rowptr.device)
+    check(lib().h2_hop2_fill(n, ptr(rowptr), ptr(col), row_begin, row_end, ptr(rp2), ptr(col2), s))
+    return rp2, col2
+
+
+def sym_normalize(rowptr, col, n_cols=None, row_begin=0, deg_all=None, stream=None):
+    """normalize(., SYM_NORMALIZED) (_dataset.py:114-118) for a binary pattern.
+    Returns (val fp32 [nnz], dinv64 [n_cols], dinv32 [n_cols])."""
+    require_cuda(rowptr, col)
+    n_rows = rowptr.numel() - 1
+    n_cols = n_rows if n_cols is None else n_cols
+    dev = rowptr.device
+    rowptr = _i64(rowptr).contiguous()
+    col = col.to(torch.int32).contiguous()
+    val = torch.empty(col.numel(), dtype=torch.float32, device=dev)
+    d64 = torch.empty(n_cols, dtype=torch.float64, device=dev)
+    d32 = torch.empty(n_cols, dtype=torch.float32, device=dev)
+    check(lib().h2_sym_normalize(n_rows, n_cols, row_begin, ptr(rowptr), ptr(col), ptr(deg_all), ptr(d64), ptr(d32),
+                                 ptr(val), stream_ptr(stream)))
+    return val, d64, d32
+
+
+def rw_normalize(rowptr, stream=None):
+    """normalize(., RW_NORMALIZED) (_dataset.py:119-123) for a binary pattern: val = 1/deg_i."""
+    require_cuda(rowptr)
+    rowptr = _i64(rowptr).contiguous()
+    n = rowptr.numel() - 1
+    nnz = int(rowptr[-1].item()) if n else 0
+    val = torch.empty(nnz, dtype=torch.float32, device=rowptr.device)
+    check(lib().h2_rw_normalize(n, ptr(rowptr), ptr(val), stream_ptr(stream)))
+    return val
+
+
+def validate_csr(sp, stream=None):
+    flag = torch.zeros(1, dtype=torch.int32, device=sp.device)
+    check(lib().h2_validate_csr(sp.n_rows, sp.dense_shape[1], ptr(sp.rowptr), ptr(sp.col), ptr(flag), stream_ptr(stream)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused aggregation round
+# ------------------------------------------------------------------------------------------------------------------
+class HopPlan:
+    """Schedule of one fused round over a fixed list of hop adjacencies (built once per graph)."""
+
+    def __init__(self, hops, factored=False, stream=None):
+        if not 1 <= len(hops) <= _cabi.MAX_HOPS:
+            raise ValueError(f"between 1 and {_cabi.MAX_HOPS} hops per fused round, got {len(hops)}")
+        self.hops = list(hops)
+        self.n_rows = hops[0].n_rows
+        self.n_cols = hops[0].dense_shape[1]
+        for h in hops:
+            if h.n_rows != self.n_rows or h.dense_shape[1] != self.n_cols:
+                raise ValueError("all hop adjacencies of a round must have the same shape")
+            if factored and h.dinv is None:
+                raise ValueError("factored mode needs SparseTensor.dinv on every hop")
+        self.factored = factored
+        dev = hops[0].device
+        self._desc = (HopDesc * len(hops))()
+        self._fill_desc([0] * len(hops))
+        L = lib()
+        self._plan_host = ctypes.create_string_buffer(L.h2_plan_host_bytes())
+        self._plan_dev = torch.empty(L.h2_plan_dev_bytes(self.n_rows, len(hops)), dtype=torch.uint8, device=dev)
+        ws_bytes = L.h2_plan_workspace_bytes(self.n_rows, len(hops))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.h2_plan_build(self.n_rows, len(hops), self._desc, ctypes.addressof(self._plan_host), ptr(self._plan_dev),
+                              ptr(ws), ws_bytes, stream_ptr(stream)))
+        self.nnz = sum(h.nnz for h in hops)
+
+    def _fill_desc(self, offsets):
+        for k, (h, off) in enumerate(zip(self.hops, offsets)):
+            d = self._desc[k]
+            d.rowptr, d.col = ptr(h.rowptr), ptr(h.col)
+            if self.factored:
+                d.val, d.dinv = None, ptr(h.dinv)
+                d.dinv_row = h.dinv.data_ptr() + 4 * h.row_begin
+            else:
+                d.val, d.dinv, d.dinv_row = ptr(h.values), None, None
+            d.out_col_off = off
+
+    def run(self, x, out, offsets, d=None, stream=None):
+        """out[:, offsets[h] : offsets[h]+d] = hops[h] @ x[:, :d]   (x, out may be column slices of one buffer)."""
+        require_cuda(x, out)
+        if x.dtype != torch.float32 or out.dtype != torch.float32:
+            raise ValueError("fused round computes in fp32")
+        if x.stride(-1) != 1 or out.stride(-1) != 1:
+            raise ValueError("x / out must be row-major (unit column stride)")
+        d = x.shape[1] if d is None else d
+        if x.shape[0] != self.n_cols or out.shape[0] != self.n_rows:
+            raise ValueError(f"shape mismatch: x {tuple(x.shape)}, out {tuple(out.shape)}, adjacency "
+                             f"[{self.n_rows}, {self.n_cols}]")
+        self._fill_desc(offsets)
+        check(lib().h2_fused_hops_spmm_f32(ctypes.addressof(self._plan_host), ptr(self._plan_dev), self.n_rows,
+                                           len(self.hops), self._desc, d, ptr(x), x.stride(0), ptr(out), out.stride(0),
+                                           stream_ptr(stream)))
+        return out
+
+
+def sparse_dense(feat, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None):
+    """SparseDense.call (_layers.py:45-52) [+ReLU]: out[:, off:off+p] = act(feat @ weight + bias)."""
+    require_cuda(weight, bias, out)
+    n, p = feat.n_rows, weight.shape[1]
+    if feat.dense_shape[1] != weight.shape[0]:
+        raise ValueError(f"feature dim {feat.dense_shape[1]} != kernel rows {weight.shape[0]}")
+    weight = weight.contiguous()
+    if out is None:
+        out = torch.empty(n, p, dtype=torch.float32, device=weight.device)
+    check(lib().h2_sparse_dense_f32(n, ptr(feat.rowptr), ptr(feat.col), ptr(feat.values), ptr(weight), p, ptr(bias),
+                                    int(relu), ptr(out), out.stride(0), out_col_off, stream_ptr(stream)))
+    return out
+
+
+def dense(x, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None):
+    """keras Dense (H2GCN.py:244-249): out[:, off:off+c] = act(x @ weight + bias), fp32."""
+    require_cuda(x, weight, bias, out)
+    n, k = x.shape
+    c = weight.shape[1]
+    if weight.shape[0] != k:
+        raise ValueError(f"input dim {k} != kernel rows {weight.shape[0]}")
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    weight = weight.contiguous()
+    if out is None:
+        out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    check(lib().h2_dense_f32(n, k, c, ptr(x), x.stride(0), ptr(weight), ptr(bias), int(relu), ptr(out), out.stride(0),
+                             out_col_off, stream_ptr(stream)))
+    return out
+
+
+def relu_slice(x, out=None, relu=True, stream=None):
+    require_cuda(x, out)
+    n, d = x.shape
+    if out is None:
+        out = torch.empty(n, d, dtype=torch.float32, device=x.device)
+    check(lib().h2_relu_slice_f32(n, d, ptr(x), x.stride(0), ptr(out), out.stride(0), int(relu), stream_ptr(stream)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host-buffer (end-to-end) graph handle
+# ------------------------------------------------------------------------------------------------------------------
+class HostGraph:
+    """h2_graph_*: adjacency resident on the device, X in / Y out through HOST buffers every call (bench.py e2e)."""
+
+    def __init__(self, hops_host, n_rows, n_cols, d_max):
+        """hops_host: list of (rowptr int64, col int32, val fp32) numpy arrays."""
+        import numpy as np
+        self._keep = [(np.ascontiguousarray(r, dtype=np.int64), np.ascontiguousarray(c, dtype=np.int32),
+                       np.ascontiguousarray(v, dtype=np.float32)) for r, c, v in hops_host]
+        H = len(self._keep)
+        arr = lambda k: (ctypes.c_void_p * H)(*[a[k].ctypes.data for a in self._keep])
+        self._h = ctypes.c_void_p()
+        self.n_rows, self.n_cols, self.n_hops = n_rows, n_cols, H
+        check(lib().h2_graph_create(n_rows, n_cols, H, arr(0), arr(1), arr(2), d_max, ctypes.byref(self._h)))
+
+    def round(self, x_host, y_host, stream=None):
+        """x_host [n_cols, d] / y_host [n_rows, H*d]: (pinned) host torch tensors or numpy arrays, fp32, contiguous."""
+        d = x_host.shape[1]
+        xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
+        yp = y_host.data_ptr() if hasattr(y_host, "data_ptr") else y_host.ctypes.data
+        check(lib().h2_graph_round_host(self._h, d, xp, yp, stream_ptr(stream)))
+        return y_host
+
+    def close(self):
+        if self._h:
+            lib().h2_graph_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

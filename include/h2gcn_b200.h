@@ -1,0 +1,153 @@
+/* h2gcn_b200 — C-ABI of the B200-native H2GCN aggregation hot path.
+ *
+ * The reference (GemsLab/H2GCN) has no FFI layer: the path is Python calling TensorFlow / scipy.  Every entry
+ * point below replaces one call site of the reference (paths relative to /root/reference/);
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add at each of them.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  All pointers are DEVICE pointers unless the name ends in
+ *    `_host`.  The caller owns every buffer; the library never allocates device memory behind the caller's back
+ *    (workspace size queries + caller-provided workspaces).  The one exception is the `h2_graph_*` handle used by
+ *    the host-buffer (end-to-end) entry points, which owns its device copies explicitly and is freed explicitly.
+ *  - every function returns an int status (H2_OK == 0); nothing throws or aborts.  h2_last_error() returns a
+ *    thread-local message for the last non-zero status.
+ *  - every device function takes a CUDA stream (`void*` == cudaStream_t), enqueues and returns.  Only functions whose
+ *    doc says "SYNCHRONISES" wait for the stream (they return a size the host needs).
+ *  - CSR: rowptr is int64 [n+1] (a shard's hop-2 pattern can exceed 2^31 entries), col is int32, val is fp32.
+ *    Column indices inside a row are ascending (tf.sparse.reorder order, h2gcn/datasets/_dataset.py:535).
+ *  - dense matrices are row-major with an explicit leading dimension in ELEMENTS (so a kernel can read and write
+ *    column slices of the zero-copy concat buffer).
+ */
+#ifndef H2GCN_B200_H
+#define H2GCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2_ABI_VERSION 1
+
+enum {
+    H2_OK = 0,
+    H2_ERR_INVALID = 1,     /* bad argument (null pointer, negative size, too many hops, ...)        -> ValueError  */
+    H2_ERR_ALIGN = 2,       /* pointer / leading dimension / offset not aligned as documented          -> ValueError  */
+    H2_ERR_WORKSPACE = 3,   /* caller-provided workspace too small                                      -> ValueError  */
+    H2_ERR_CUDA = 4,        /* a CUDA runtime call failed (message has cudaGetErrorString)              -> RuntimeError */
+    H2_ERR_UNSUPPORTED = 5, /* shape outside what the kernels cover                                     -> ValueError  */
+    H2_ERR_INDEX = 6        /* h2_validate_csr found an out-of-range / unsorted column                  -> ValueError  */
+};
+
+#define H2_MAX_HOPS 8
+
+typedef void *h2_stream_t; /* cudaStream_t */
+
+/* One normalised hop adjacency \bar{A}_h as the reference hands it to GCNLayer (a tf.SparseTensor, row-major sorted;
+ * h2gcn/datasets/_dataset.py:528-535), in CSR form, plus where its product lands in the output row:
+ * out[i, out_col_off : out_col_off + d] = sum_k val[k] * X[col[k], :]   (tf.stack(axis=-2) + Flatten column order,
+ * h2gcn/models/_layers.py:78-81, h2gcn/models/H2GCN.py:271-272). */
+typedef struct {
+    const int64_t *rowptr; /* [n+1] */
+    const int32_t *col;    /* [nnz] */
+    const float *val;      /* [nnz] explicit fp32 values (reference semantics) or NULL => factored: val = dinv[i]*dinv[j] */
+    const float *dinv;     /* [n_cols] column scale, only read when val == NULL */
+    const float *dinv_row; /* [n_rows] row scale of the LOCAL rows (= dinv + row_begin), only read when val == NULL */
+    int64_t out_col_off;   /* column offset (elements) inside the output row */
+} h2_hop_t;
+
+/* ---- library / errors -------------------------------------------------------------------------------------- */
+int h2_abi_version(void);
+const char *h2_last_error(void);
+/* number of kernels of THIS library launched by the calling process since load (bench.py's gpu_launches). */
+int64_t h2_launch_count(void);
+
+/* ---- a1..a4: adjacency-power precompute ---------------------------------------------------------------------
+ * replaces TransformSPAdj.removeEye / nhoodSplit / normalize + sparse2Tensor,
+ * h2gcn/datasets/_dataset.py:132-136, 138-158, 109-124, 528-535 as called from getTensors :559-576. */
+
+/* removeEye: drops the diagonal entries of a CSR matrix; two calls: count (writes rowcount_out[n]), then fill
+ * (val_in / val_out optional: NULL for a pure pattern). */
+int h2_remove_eye_count(int32_t n, const int64_t *rowptr, const int32_t *col, int64_t *rowcount_out, h2_stream_t s);
+int h2_remove_eye_fill(int32_t n, const int64_t *rowptr, const int32_t *col, const float *val_in,
+                       const int64_t *rowptr_out, int32_t *col_out, float *val_out, h2_stream_t s);
+
+/* exclusive prefix sum of int64 counts[n] into rowptr[n+1] (rowptr[0]=0).  ws from h2_scan_workspace_bytes. */
+size_t h2_scan_workspace_bytes(int64_t n);
+int h2_exclusive_scan_i64(int64_t n, const int64_t *counts, int64_t *rowptr, void *ws, size_t ws_bytes, h2_stream_t s);
+
+/* nhoodSplit for nhood = 2: pattern of vertices at distance EXACTLY 2, bin((A+I)^2) - bin(A+I).
+ * `rowptr/col` = A without self loops, rows sorted, LOCAL rows [row_begin, row_end) of a graph with n vertices are
+ * produced (row sharding, SURVEY.md §8e: the full A is replicated, output rows are local).
+ * count: rowcount2[row_end-row_begin];  fill: col2 ascending inside each row (tf.sparse.reorder order for free). */
+int h2_hop2_count(int32_t n, const int64_t *rowptr, const int32_t *col, int32_t row_begin, int32_t row_end,
+                  int64_t *rowcount2, h2_stream_t s);
+int h2_hop2_fill(int32_t n, const int64_t *rowptr, const int32_t *col, int32_t row_begin, int32_t row_end,
+                 const int64_t *rowptr2, int32_t *col2, h2_stream_t s);
+
+/* normalize(., SYM_NORMALIZED) for a binary pattern: deg = row count (global degree vector supplied by the caller
+ * when rows are sharded: `deg_all` [n_cols] int64, or NULL => computed from rowptr, requires n_rows == n_cols);
+ * dinv64[i] = deg^-1/2 with inf -> 0 (the degree mask, _dataset.py:115-116); val[k] = fp32((dinv_i * 1.0) * dinv_j)
+ * evaluated in fp64 (left-associated like `DInvSqrt @ adj @ DInvSqrt`, :117-118, then X.data.astype(float32), :535).
+ * Any of dinv64 / dinv32 / val may be NULL to skip that output.  row_begin = global index of local row 0. */
+int h2_sym_normalize(int32_t n_rows, int32_t n_cols, int32_t row_begin, const int64_t *rowptr, const int32_t *col,
+                     const int64_t *deg_all, double *dinv64, float *dinv32, float *val, h2_stream_t s);
+/* RW_NORMALIZED (_dataset.py:119-123): val = fp32(1/deg_i), inf -> 0. */
+int h2_rw_normalize(int32_t n_rows, const int64_t *rowptr, float *val, h2_stream_t s);
+
+/* debug-mode validation: columns in [0, n_cols), strictly ascending inside each row, rowptr monotone.
+ * `flag_dev` is a caller-owned device int32 scratch word.  SYNCHRONISES.  Returns H2_ERR_INDEX on a violation
+ * (TF raises InvalidArgumentError for the same on CPU). */
+int h2_validate_csr(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, int32_t *flag_dev,
+                    h2_stream_t s);
+
+/* ---- a6+a7+a8: the fused aggregation round ------------------------------------------------------------------
+ * replaces GCNLayer.sparse_dense_matmul / GCNLayer.call (h2gcn/models/_layers.py:62-81) + Flatten (H2GCN.py:271-272)
+ * + the copies of ConcatLayer.call (_layers.py:90-96) by writing every hop straight into its column slot.
+ *
+ * The schedule ("plan") depends only on the sparsity structure and is built once per graph, like the reference's
+ * once-per-process tensors (H2GCN.py:54).  h2_plan_build SYNCHRONISES (it returns the launch geometry in the plan
+ * header, which lives on the host inside the caller's `plan_host` buffer of h2_plan_host_bytes() bytes); the device
+ * part of the plan lives in the caller's `plan_dev` buffer of h2_plan_dev_bytes(n_rows, n_hops) bytes. */
+size_t h2_plan_host_bytes(void);
+size_t h2_plan_dev_bytes(int32_t n_rows, int32_t n_hops);
+size_t h2_plan_workspace_bytes(int32_t n_rows, int32_t n_hops);
+int h2_plan_build(int32_t n_rows, int32_t n_hops, const h2_hop_t *hops_host, void *plan_host, void *plan_dev,
+                  void *ws, size_t ws_bytes, h2_stream_t s);
+
+/* Y[i, hop.out_col_off : +d] = \bar{A}_hop[i, :] . X   for every hop, one launch.
+ * X: [n_cols, d] fp32 with leading dimension ldx; Y: [n_rows, *] fp32 with leading dimension ldy.  X and Y may be
+ * disjoint column slices of the same buffer.  Requires d % 4 == 0, ldx % 4 == 0, ldy % 4 == 0, out_col_off % 4 == 0
+ * and 16-byte aligned X / Y (H2_ERR_ALIGN otherwise).  The hops must be the ones the plan was built from. */
+int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_dev, int32_t n_rows, int32_t n_hops,
+                           const h2_hop_t *hops_host, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                           h2_stream_t s);
+
+/* ---- a5 / a10: dense ends writing into the concat buffer ----------------------------------------------------
+ * replaces SparseDense.call (+ReLU) (_layers.py:45-52, H2GCN.py:269-270): Y[:, off:off+p] = act(Xs . W + b),
+ * Xs CSR [n, F] fp32 (row-major sorted COO in the reference), W [F, p] row-major. */
+int h2_sparse_dense_f32(int32_t n_rows, const int64_t *rowptr, const int32_t *col, const float *val, const float *W,
+                        int32_t p, const float *bias, int32_t relu, float *Y, int64_t ldy, int64_t out_col_off,
+                        h2_stream_t s);
+/* replaces keras Dense (H2GCN.py:244-249): Y[n, c] = act(X[n, k] . W[k, c] + b), fp32 SIMT (parity mode). */
+int h2_dense_f32(int32_t n_rows, int32_t k, int32_t c, const float *X, int64_t ldx, const float *W, const float *bias,
+                 int32_t relu, float *Y, int64_t ldy, int64_t out_col_off, h2_stream_t s);
+/* ReLU / copy of a column slice (layers the planner could not fuse away). */
+int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t relu,
+                      h2_stream_t s);
+
+/* ---- end-to-end entry points with HOST buffers (bench.py `e2e`, the call a CPU-side caller makes) ------------
+ * The graph (all hops + plan) is uploaded once (h2_graph_create, like getTensors runs once per process); every
+ * h2_graph_round_host call copies X host->device, runs the fused round and copies Y device->host on `s`, then
+ * SYNCHRONISES.  x_host / y_host should be pinned for full PCIe speed but need not be. */
+typedef struct h2_graph h2_graph_t;
+int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
+                    const int32_t *const *col_host, const float *const *val_host, int32_t d_max, h2_graph_t **out);
+int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s);
+int h2_graph_destroy(h2_graph_t *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2GCN_B200_H */

@@ -1,0 +1,303 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C-ABI (h2gcn_b200.ops ->
+ctypes -> libh2gcn_b200.so) and is compared with the CPU oracle and the committed golden vectors.
+
+Bars: indices / degree masks bit-exact; fp32 adjacency values bit-exact (fp64 product rounded once); SpMM outputs and
+activations within 1e-4 relative (of the max-abs of the reference tensor) — the north-star tolerance."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from h2gcn_b200 import _cabi
+    _cabi.lib()  # fails loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def _oracle():
+    from oracle import cbind
+    from oracle import h2gcn_oracle as O
+    return O, cbind
+
+
+def _sparse(rows, cols, vals, n, dev):
+    from h2gcn_b200.ops import SparseTensor
+    rp, cc = util.coo_to_csr(rows, cols, n)
+    return SparseTensor(torch.from_numpy(rp).to(dev), torch.from_numpy(cc).to(dev),
+                        torch.from_numpy(np.asarray(vals, dtype=np.float32)).to(dev), (n, n))
+
+
+# ---- a1-a4 precompute --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.all_golden_names())
+def test_precompute_matches_reference_bit_exact(dev, name):
+    from h2gcn_b200.datasets._dataset import GraphData
+    z = util.load_golden(name)
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    with np.errstate(divide="ignore"):
+        data.row_normalize_features()
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=[str(s) for s in z["hops_spec"]])
+    idx = t.adj.indices.cpu().numpy()
+    assert np.array_equal(idx[:, 0], z["adjre_rows"]) and np.array_equal(idx[:, 1], z["adjre_cols"])
+    fi = t.features.indices.cpu().numpy()
+    assert np.array_equal(fi[:, 0], z["featn_rows"]) and np.array_equal(fi[:, 1], z["featn_cols"])
+    assert np.array_equal(t.features.values.cpu().numpy(), z["featn_vals"])
+    assert len(t.adj_hops) == len(util.golden_hops(z))
+    for hop, (gr, gc, gv) in zip(t.adj_hops, util.golden_hops(z)):
+        hi = hop.indices.cpu().numpy()
+        assert np.array_equal(hi[:, 0], gr) and np.array_equal(hi[:, 1], gc), "hop pattern must be bit-exact"
+        got = hop.values.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), gv.view(np.uint32)), "fp32 adjacency values must be bit-exact"
+        deg = np.bincount(gr, minlength=hop.n_rows)
+        assert np.array_equal(hop.dinv.cpu().numpy() == 0, deg == 0), "zero-degree mask"
+        from h2gcn_b200 import ops
+        ops.validate_csr(hop)
+
+
+@pytest.mark.parametrize("name", ["tiny_tri_tail_merged", "tiny_rand40_merged"])
+def test_merged_hop_spec(dev, name):
+    from h2gcn_b200.datasets._dataset import GraphData
+    z = util.load_golden(name)
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=[str(s) for s in z["hops_spec"]])
+    for hop, (gr, gc, gv) in zip(t.adj_hops, util.golden_hops(z)):
+        hi = hop.indices.cpu().numpy()
+        assert np.array_equal(hi[:, 0], gr) and np.array_equal(hi[:, 1], gc)
+        assert np.array_equal(hop.values.cpu().numpy(), gv)
+
+
+@pytest.mark.parametrize("gen,args", [("uniform_graph", (3000, 20000)), ("preferential_attachment", (4000, 5)),
+                                      ("rmat_graph", (5000, 60000))])
+def test_hop2_pattern_vs_oracle_synthetic(dev, gen, args):
+    from h2gcn_b200 import ops
+    from h2gcn_b200.utils import synth
+    O, cbind = _oracle()
+    a = getattr(synth, gen)(*args)
+    rp = torch.from_numpy(a.indptr.astype(np.int64)).to(dev)
+    col = torch.from_numpy(a.indices.astype(np.int32)).to(dev)
+    rp2, col2 = ops.hop2_pattern(rp, col)
+    ref_rp, ref_col = cbind.hop2_csr(a.indptr, a.indices)
+    assert np.array_equal(rp2.cpu().numpy(), ref_rp) and np.array_equal(col2.cpu().numpy(), ref_col)
+    # sharded rows give the same rows
+    lo, hi = a.shape[0] // 3, 2 * a.shape[0] // 3
+    rps, cols = ops.hop2_pattern(rp, col, lo, hi)
+    assert np.array_equal(cols.cpu().numpy(), ref_col[ref_rp[lo]:ref_rp[hi]])
+    assert np.array_equal(rps.cpu().numpy(), ref_rp[lo:hi + 1] - ref_rp[lo])
+    # values: fp64 product rounded once
+    val, d64, d32 = ops.sym_normalize(rp2, col2)
+    ref = O.sym_normalize(sp.csr_matrix((np.ones(len(ref_col)), ref_col, ref_rp), shape=a.shape))[0]
+    assert np.array_equal(val.cpu().numpy(), ref.data.astype(np.float32))
+
+
+def test_remove_eye_and_empty_inputs(dev):
+    from h2gcn_b200 import ops
+    from h2gcn_b200.datasets._dataset import TransformSPAdj
+    TransformSPAdj.device = dev
+    a = sp.csr_matrix(np.array([[1, 1, 0], [1, 0, 0], [0, 0, 2]], dtype=np.float32))
+    b = TransformSPAdj.removeEye(a)
+    assert (b.toarray() == np.array([[0, 1, 0], [1, 0, 0], [0, 0, 0]])).all() and b.nnz == 2
+    # edgeless graph: [I, empty]; single edge: no 2-hop ring -> short list (reference :151-153)
+    assert len(TransformSPAdj.nhoodSplit(sp.csr_matrix((4, 4), dtype=np.float32), 2)) == 2
+    e = sp.csr_matrix(np.array([[0, 1], [1, 0]], dtype=np.float32))
+    assert len(TransformSPAdj.nhoodSplit(e, 2)) == 2
+    z = torch.zeros(0, dtype=torch.int64, device=dev)
+    assert ops.exclusive_scan(z).tolist() == [0]
+
+
+# ---- a6-a8 fused round ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.all_golden_names())
+@pytest.mark.parametrize("d", [4, 16, 64, 100, 128, 256])
+def test_fused_round_vs_oracle_golden_graphs(dev, name, d):
+    from h2gcn_b200.ops import HopPlan
+    O, cbind = _oracle()
+    z = util.load_golden(name)
+    n = int(z["feat_shape"][0])
+    hops = util.golden_hops(z)
+    x = np.random.default_rng(d).standard_normal((n, d)).astype(np.float32)
+    ref = O.fused_round(hops, x)
+    plan = HopPlan([_sparse(r, c, v, n, dev) for r, c, v in hops])
+    xd = torch.from_numpy(x).to(dev)
+    y = torch.full((n, 2 * d), float("nan"), device=dev)
+    plan.run(xd, y, [0, d])
+    assert util.rel_err(y.cpu().numpy(), ref) <= TOL
+    # zero-degree rows are written as exact zeros (TF zero-initialises its output)
+    deg2 = np.bincount(hops[1][0], minlength=n)
+    assert (y[:, d:].cpu().numpy()[deg2 == 0] == 0).all()
+
+
+def test_fused_round_strided_zero_copy_buffer(dev):
+    """x and y are column slices of ONE buffer laid out like the H2GCN-2 concat buffer [r2 | r0 | r1]."""
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    z = util.load_golden("planetoid_cora")
+    n, p = int(z["feat_shape"][0]), 64
+    hops = util.golden_hops(z)
+    plan = HopPlan([_sparse(r, c, v, n, dev) for r, c, v in hops])
+    r0 = np.random.default_rng(0).standard_normal((n, p)).astype(np.float32)
+    buf = torch.zeros(n, 7 * p, device=dev)
+    buf[:, 4 * p:5 * p] = torch.from_numpy(r0).to(dev)
+    plan.run(buf[:, 4 * p:5 * p], buf, [5 * p, 6 * p], d=p)             # round 1 -> r1 slot
+    plan.run(buf[:, 5 * p:7 * p], buf, [0, 2 * p], d=2 * p)             # round 2 -> r2 slot
+    r1 = O.fused_round(hops, r0)
+    r2 = O.fused_round(hops, r1)
+    ref = np.concatenate([r2, r0, r1], axis=1)
+    assert util.rel_err(buf.cpu().numpy(), ref) <= TOL
+
+
+def test_fused_round_factored_mode(dev):
+    """val == NULL: the kernel rebuilds dinv_i * dinv_j from the degree vector (index-only CSR, half the bytes)."""
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    z = util.load_golden("planetoid_citeseer")
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    n, d = t.adj.n_rows, 64
+    x = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
+    y = torch.empty(n, 2 * d, device=dev)
+    HopPlan(t.adj_hops, factored=True).run(torch.from_numpy(x).to(dev), y, [0, d])
+    assert util.rel_err(y.cpu().numpy(), O.fused_round(util.golden_hops(z), x)) <= TOL
+
+
+def test_long_rows_use_cta_path_and_are_deterministic(dev):
+    """A star graph has one row of n-1 entries (CTA-row path) and its 2-hop pattern is dense among the leaves."""
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    n, d = 1500, 128
+    rows = np.zeros(n - 1, dtype=np.int64)
+    cols = np.arange(1, n, dtype=np.int64)
+    a = sp.csr_matrix((np.ones(2 * (n - 1), dtype=np.float32), (np.r_[rows, cols], np.r_[cols, rows])), shape=(n, n))
+    data = GraphData(a, sp.identity(n, dtype=np.float32, format="csr"), device=dev)
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    assert t.adj_hops[1].nnz == (n - 1) * (n - 2)
+    x = np.random.default_rng(2).standard_normal((n, d)).astype(np.float32)
+    xd = torch.from_numpy(x).to(dev)
+    plan = HopPlan(t.adj_hops)
+    y1 = torch.empty(n, 2 * d, device=dev)
+    y2 = torch.empty(n, 2 * d, device=dev)
+    plan.run(xd, y1, [0, d])
+    plan.run(xd, y2, [0, d])
+    assert torch.equal(y1, y2), "no atomics: bit-reproducible"
+    hops = [(h.indices[:, 0].cpu().numpy(), h.indices[:, 1].cpu().numpy(), h.values.cpu().numpy()) for h in t.adj_hops]
+    assert util.rel_err(y1.cpu().numpy(), O.fused_round(hops, x)) <= TOL
+
+
+def test_fused_round_argument_errors(dev):
+    from h2gcn_b200.ops import HopPlan
+    z = util.load_golden("tiny_path4")
+    hops = util.golden_hops(z)
+    plan = HopPlan([_sparse(r, c, v, 4, dev) for r, c, v in hops])
+    x = torch.zeros(4, 6, device=dev)
+    with pytest.raises(ValueError):   # d % 4 != 0
+        plan.run(x, torch.zeros(4, 12, device=dev), [0, 6])
+    with pytest.raises(ValueError):   # wrong height
+        plan.run(torch.zeros(5, 8, device=dev), torch.zeros(4, 16, device=dev), [0, 8])
+    with pytest.raises(RuntimeError):  # host tensor: no CPU fallback
+        plan.run(torch.zeros(4, 8), torch.zeros(4, 16, device=dev), [0, 8])
+
+
+def test_linearity_and_row_scaling_at_full_size(dev):
+    """Size-independent properties at the north-star size (|V|=10k, |E|=200k, d=128), where the Python oracle is too
+    slow: linearity in X, and agreement of explicit-value and factored modes; plus a row sample against the C oracle."""
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.ops import HopPlan
+    from h2gcn_b200.utils import synth
+    _, cbind = _oracle()
+    n, d = 10000, 128
+    a = synth.uniform_graph(n, 200000, seed=0)
+    data = GraphData(a, sp.identity(n, dtype=np.float32, format="csr"), device=dev)
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    assert t.adj_hops[0].nnz == 400000
+    plan = HopPlan(t.adj_hops)
+    x1 = torch.from_numpy(synth.features(n, d, 0)).to(dev)
+    x2 = torch.from_numpy(synth.features(n, d, 1)).to(dev)
+    y1, y2, y12 = (torch.empty(n, 2 * d, device=dev) for _ in range(3))
+    plan.run(x1, y1, [0, d])
+    plan.run(x2, y2, [0, d])
+    plan.run(2 * x1 - 3 * x2, y12, [0, d])
+    assert util.rel_err(y12.cpu().numpy(), (2 * y1 - 3 * y2).cpu().numpy()) <= TOL
+    yf = torch.empty(n, 2 * d, device=dev)
+    HopPlan(t.adj_hops, factored=True).run(x1, yf, [0, d])
+    assert util.rel_err(yf.cpu().numpy(), y1.cpu().numpy()) <= TOL
+    h = t.adj_hops
+    ref = cbind.fused_round(h[0].rowptr.cpu().numpy(), h[0].col.cpu().numpy(), h[0].values.cpu().numpy(),
+                            h[1].rowptr.cpu().numpy(), h[1].col.cpu().numpy(), h[1].values.cpu().numpy(),
+                            x1.cpu().numpy())
+    assert util.rel_err(y1.cpu().numpy(), ref) <= TOL
+
+
+def test_host_buffer_entry_point(dev):
+    """h2_graph_* : X in / Y out through host buffers (the e2e path of bench.py)."""
+    from h2gcn_b200.ops import HostGraph
+    O, _ = _oracle()
+    z = util.load_golden("planetoid_cora")
+    n, d = int(z["feat_shape"][0]), 64
+    hops = util.golden_hops(z)
+    g = HostGraph([(util.coo_to_csr(r, c, n)[0], c, v) for r, c, v in hops], n, n, d_max=128)
+    x = torch.from_numpy(np.random.default_rng(5).standard_normal((n, d)).astype(np.float32)).pin_memory()
+    y = torch.empty(n, 2 * d).pin_memory()
+    g.round(x, y)
+    assert util.rel_err(y.numpy(), O.fused_round(hops, x.numpy())) <= TOL
+    g.close()
+
+
+# ---- a5, a9-a11 full forward -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", util.all_golden_names())
+def test_forward_matches_reference_activations(dev, name):
+    """H2GCN(...)(adj, features, adj_hops) with the reference's weights: logits and every saved activation."""
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.models import parse_network_setup
+    from h2gcn_b200.models.H2GCN import H2GCN
+    z = util.load_golden(name)
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    with np.errstate(divide="ignore"):
+        data.row_normalize_features()
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    for setup in util.setups_in(z):
+        conf = parse_network_setup(str(z[f"{setup}/setup"]), int(z["num_labels"]), _dense_units=64, _dropout_rate=0.5)
+        model = H2GCN(conf)
+        model.set_weights(util.weights_of(z, setup), device=dev)
+        logits = model(t.adj, t.features, t.adj_hops, training=False)            # fused program
+        assert util.rel_err(logits.cpu().numpy()[::41], z[f"{setup}/logits_rows"]) <= TOL, setup
+        acts = {}
+        logits_i = model(t.adj, t.features, t.adj_hops, training=False, saveActivations=acts)   # interpreter
+        assert util.rel_err(logits_i.cpu().numpy(), logits.cpu().numpy()) <= TOL
+        for nm in [str(s) for s in z[f"{setup}/act_names"]]:
+            a = np.asarray(acts[f"activations/{nm}"])
+            assert tuple(a.shape) == tuple(z[f"{setup}/act/{nm}/shape"]), (setup, nm)
+            a2 = a.reshape(a.shape[0], -1)
+            assert util.rel_err(a2[::41], z[f"{setup}/act/{nm}/rows"]) <= TOL, (setup, nm)
+            s = z[f"{setup}/act/{nm}/sum"]
+            assert abs(a2.astype(np.float64).sum() - s[0]) <= TOL * max(1.0, s[1]), (setup, nm)
+
+
+def test_fused_program_is_used_and_counts_launches(dev):
+    from h2gcn_b200 import _cabi
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.models import parse_network_setup
+    from h2gcn_b200.models.H2GCN import H2GCN
+    z = util.load_golden("planetoid_cora")
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    model = H2GCN(parse_network_setup("M64-R-T1-G-V-T2-G-V-C1-C2-D0.5-MO", 7))
+    model(t.adj, t.features, t.adj_hops)
+    before = _cabi.launch_count()
+    out = model(t.adj, t.features, t.adj_hops)
+    assert _cabi.launch_count() - before == 4, "X.W0+relu, round 1, round 2, classifier"
+    assert out.shape == (2708, 7)
+    emb_model = H2GCN(parse_network_setup("M64-E-R-T1-G-V-C1-MO", 7))
+    assert emb_model.getEmbeddings(t.adj, t.features, t.adj_hops).shape == (2708, 64)
