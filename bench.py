@@ -156,6 +156,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--factored", action="store_true", help="index-only CSR (val = dinv_i*dinv_j rebuilt in-kernel)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "csr", "tensor"],
+                    help="hop storage: auto = by density (dense-ish hops on tcgen05), csr = fp32 gather everywhere")
+    ap.add_argument("--splits", type=int, default=2, help="bf16 pieces of X on the tensor-core path (2 or 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,7 +184,7 @@ def main():
     n = N_PER_GPU * world
     adj = build_workload(n, E_PER_GPU * world, seed=0)
     t0 = time.perf_counter()
-    g = ShardedGraph(adj, rank, world, dev, factored=args.factored)
+    g = ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=args.splits)
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0
     d = FEAT
@@ -275,7 +278,7 @@ def main():
                                f"({'factored dinv' if args.factored else 'explicit fp32'} adjacency values), seed 0, "
                                f"rows sharded over {world} GPU(s)",
                    "n_vertices": n, "nnz1": g.nnz1_global, "nnz2_local": g.nnz2_local, "nnz_local": g.nnz_local,
-                   "nnz_total": nnz_total, "max_row_nnz": g.max_row_nnz, "kernel": g.kernel_name,
+                   "nnz_total": nnz_total, "max_row_nnz": g.max_row_nnz, "kernel": g.plan.kernel_name,
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write); each step timed by its own CUDA "
                          "event pair, ms_per_step = sum/K (max over ranks)",
                    "precompute_s": t_pre, "ms_per_step_min": float(times.min()), "ms_per_step_median": float(np.median(times)),

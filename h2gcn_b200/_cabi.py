@@ -41,6 +41,15 @@ PROTOTYPES = {
     "h2_plan_build": (ctypes.c_int, [c_i32, c_i32, ctypes.POINTER(HopDesc), c_vp, c_vp, c_vp, c_sz, c_vp]),
     "h2_fused_hops_spmm_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(HopDesc), c_i32, c_vp, c_i64,
                                               c_vp, c_i64, c_vp]),
+    "h2_bm_host_bytes": (c_sz, []),
+    "h2_bm_index_bytes": (c_sz, [c_i32, c_i32]),
+    "h2_bm_count": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, ctypes.POINTER(c_i64), c_vp]),
+    "h2_bm_plan_dev_bytes": (c_sz, [c_i32, c_i32, c_i64]),
+    "h2_bm_fill": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "h2_bm_xpack_bytes": (c_sz, [c_i32, c_i32, c_i32]),
+    "h2_bm_partial_bytes": (c_sz, [c_vp, c_i32, c_i32]),
+    "h2_bm_pack_x_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "h2_bm_spmm_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "h2_sparse_dense_f32": (ctypes.c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
     "h2_dense_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
     "h2_relu_slice_f32": (ctypes.c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),

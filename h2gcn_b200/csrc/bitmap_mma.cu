@@ -1,0 +1,629 @@
+// Dense-ish hop adjacency on the 5th-gen tensor cores.
+//
+// The exact-2-hop pattern P2 of a graph with average degree ~40 is 10-15 % dense at |V| = 10 k: a CSR gather has to
+// pull nnz x 512 B through L2 (7.6 GB per round, profiles/r01a) although X itself is only 5 MB.  P2 is BINARY, so it
+// is exactly representable in bf16; with the symmetric normalisation factored out,
+//     Y = diag(dinv) . P . (diag(dinv) . X),
+// the product P . X' is a dense contraction over a 0/1 matrix that `tcgen05.mma` evaluates exactly, given X' split
+// into bf16 pieces (hi + lo [+ lo2]: 16 [24] significand bits; the fp32 accumulators live in TMEM).
+//
+// Format ("tile bitmap"): P is cut into units of 256 rows x 64 columns; only non-empty units are stored, each as
+// 256 x uint64 (2 KB, 1 bit per entry instead of a 4-byte column index).  Units are ordered by (row tile, column
+// chunk).  A persistent grid of <= 148 CTAs gets equal contiguous ranges of units ("stream-K"); a range that does
+// not cover a whole row tile writes an fp32 partial tile that a fix-up kernel adds in a fixed order (deterministic).
+//
+// Per CTA (320 threads, 1 CTA / SM, ~193 KB shared memory, all 512 TMEM columns):
+//   warp 0      : TMA producer — one `cp.async.bulk` (1-D TMA, UBLKCP) per unit copies the pre-packed, pre-swizzled
+//                 32 KB X' tile [S*DG rows x 64 k] into the stage, completing on the stage's mbarrier.
+//   warp 1      : allocates TMEM, then a single elected thread issues 2 x 4 `tcgen05.mma.cta_group::1.kind::f16`
+//                 (M=128, N=S*DG, K=16) per unit and `tcgen05.commit`s to free the stage / publish the accumulator.
+//   warps 2..9  : A producers — thread r expands the 64 bits of row r into 64 bf16 (0.0 / 1.0) and stores them as
+//                 one 128-byte row of the K-major SWIZZLE_128B operand tile; afterwards the same warps are the
+//                 epilogue: `tcgen05.ld` 32 lanes x 32 columns, hi + lo, x dinv_row, 128-bit stores.
+#include <cuda/ptx>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace h2 {
+
+constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B tile
+constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int kBmStages = 3;
+constexpr int kBmThreads = 320;  // 10 warps
+constexpr uint32_t kBmMagic = 0x48324232u;  // "H2B2"
+
+struct BmSegment {       // one contiguous run of units inside one row tile, handled by one CTA
+    int32_t tile;
+    int32_t unit_begin;  // global unit index
+    int32_t unit_end;
+    int32_t partial_slot;  // -1: covers the whole tile -> write Y directly; else index into the partial workspace
+};
+
+struct BmFix {           // one row tile whose result is the ordered sum of partial slots
+    int32_t tile;
+    int32_t slot_begin;
+    int32_t slot_end;
+    int32_t pad;
+};
+
+struct BmHost {          // host header (caller's bm_host buffer)
+    uint32_t magic;
+    int32_t n_rows, n_cols, n_tiles, n_chunks;
+    int32_t n_ctas, n_partial_slots, n_fix;
+    int64_t n_units;
+    int64_t nnz;
+    // offsets (bytes) into the device plan buffer
+    int64_t off_unit_chunk, off_bits, off_seg, off_cta_seg_ptr, off_fix, off_empty_tiles, n_empty_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// format construction
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void bm_flag_kernel(int32_t n_rows, int32_t n_chunks, const int64_t *__restrict__ rowptr,
+                               const int32_t *__restrict__ col, int64_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    const int64_t base = (row / kTileRows) * n_chunks;
+    for (int64_t k = s + lane; k < e; k += 32) flags[base + col[k] / kChunkCols] = 1;
+}
+
+__global__ void bm_fill_kernel(int32_t n_rows, int32_t n_chunks, const int64_t *__restrict__ rowptr,
+                               const int32_t *__restrict__ col, const int64_t *__restrict__ unit_index,
+                               int32_t *__restrict__ unit_chunk, unsigned long long *__restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    const int64_t base = (row / kTileRows) * n_chunks;
+    const int r = (int)(row % kTileRows);
+    for (int64_t k = s + lane; k < e; k += 32) {
+        const int c = col[k];
+        const int chunk = c / kChunkCols;
+        const int64_t u = unit_index[base + chunk];
+        atomicOr(&bits[u * kTileRows + r], 1ull << (c % kChunkCols));
+        unit_chunk[u] = chunk;  // same value from every writer
+    }
+}
+
+__global__ void bm_tile_ptr_kernel(int32_t n_tiles, int32_t n_chunks, const int64_t *__restrict__ unit_index,
+                                   int64_t *__restrict__ tile_ptr) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_tiles) tile_ptr[t] = unit_index[(int64_t)t * n_chunks];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// X' packing: fp32 X (row-major, ld) -> per 64-row chunk a [S*DG x 64] bf16 K-major tile, 128-byte swizzled, i.e.
+// byte-for-byte the shared-memory image the UMMA B descriptor expects.  n = s*DG + f, k = j % 64.
+// ------------------------------------------------------------------------------------------------------------------
+template <int DG>
+__global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d, int32_t n_groups, int32_t splits,
+                                                      const float *__restrict__ X, int64_t ldx,
+                                                      const float *__restrict__ dinv, uint4 *__restrict__ out) {
+    __shared__ float s_x[kChunkCols][DG + 1];
+    const int chunk = blockIdx.x, g = blockIdx.y;
+    const int j0 = chunk * kChunkCols, f0 = g * DG;
+    for (int idx = threadIdx.x; idx < kChunkCols * DG; idx += blockDim.x) {
+        const int k = idx / DG, f = idx % DG;
+        const int j = j0 + k;
+        float v = 0.f;
+        if (j < n_cols && f0 + f < d) v = X[(int64_t)j * ldx + f0 + f] * (dinv ? dinv[j] : 1.f);
+        s_x[k][f] = v;
+    }
+    __syncthreads();
+    const int n_rows_b = splits * DG;
+    uint4 *tile = out + ((int64_t)chunk * n_groups + g) * (n_rows_b * 8);  // 8 x 16 B per n-row
+    for (int idx = threadIdx.x; idx < n_rows_b * 8; idx += blockDim.x) {
+        const int n = idx >> 3, c16 = idx & 7;  // 16-byte chunk c16 holds k = 8*c16 .. 8*c16+7
+        const int s = n / DG, f = n % DG;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            uint32_t h[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float v = s_x[c16 * 8 + e + q][f];
+                __nv_bfloat16 b = __float2bfloat16_rn(v);
+                for (int t = 0; t < s; ++t) {  // residual after t pieces
+                    v -= __bfloat162float(b);
+                    b = __float2bfloat16_rn(v);
+                }
+                h[q] = (uint32_t)__bfloat16_as_ushort(b);
+            }
+            w[e >> 1] = h[0] | (h[1] << 16);
+        }
+        const int dst = (n >> 3) * 64 + (n & 7) * 8 + (c16 ^ (n & 7));  // in 16-byte units, 1024-byte atoms
+        tile[dst] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------------------------
+struct BmParams {
+    const int32_t *unit_chunk;
+    const unsigned long long *bits;
+    const BmSegment *seg;
+    const int32_t *cta_seg_ptr;  // [n_ctas + 1]
+    const uint4 *xpack;          // [n_chunks][n_groups][S*DG x 64] bf16 tiles
+    const float *dinv_row;       // [n_rows] (local rows) or nullptr
+    float *Y;                    // + out_col_off applied by the host
+    float *partial;              // [n_partial_slots][n_groups][256][DG]
+    int64_t ldy;
+    int32_t n_rows, d, n_groups, splits;
+};
+
+template <int DG, int S>
+__global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
+    constexpr int NB = S * DG;                      // UMMA N
+    constexpr uint32_t kABytes = kTileRows * 128;   // 32 KB: two 128-row halves
+    constexpr uint32_t kBBytes = NB * 128;
+    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kTmemCols = (2 * NB <= 32) ? 32 : (2 * NB <= 64) ? 64 : (2 * NB <= 128) ? 128 : (2 * NB <= 256) ? 256 : 512;
+    static_assert(2 * NB <= 512 && NB % 16 == 0 && NB >= 16, "UMMA N / TMEM budget");
+    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages (1024-aligned), then barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    __shared__ uint64_t s_bar[3 * kBmStages + 2];
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t bar_full_a = smem_u32(&s_bar[0]);
+    const uint32_t bar_full_b = smem_u32(&s_bar[kBmStages]);
+    const uint32_t bar_empty = smem_u32(&s_bar[2 * kBmStages]);
+    const uint32_t bar_acc_full = smem_u32(&s_bar[3 * kBmStages]);
+    const uint32_t bar_acc_empty = smem_u32(&s_bar[3 * kBmStages + 1]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg_begin = p.cta_seg_ptr[blockIdx.x], seg_end = p.cta_seg_ptr[blockIdx.x + 1];
+    const int n_work = seg_end - seg_begin;  // (segment, group) pairs are enumerated group-major inside a segment
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBmStages; ++s) {
+            mbar_init(bar_full_a + 8 * s, 8);   // one arrive per A-producer warp
+            mbar_init(bar_full_b + 8 * s, 1);   // arrive.expect_tx by the TMA thread
+            mbar_init(bar_empty + 8 * s, 1);    // tcgen05.commit
+        }
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer (B tiles) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int w = 0; w < n_work; ++w) {
+                const BmSegment sg = p.seg[seg_begin + w];
+                for (int g = 0; g < p.n_groups; ++g) {
+                    for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
+                        const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
+                        mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                        mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes);
+                        const uint4 *src = p.xpack + ((int64_t)p.unit_chunk[u] * p.n_groups + g) * (kBBytes / 16);
+                        bulk_copy_g2s(smem_base + st * kStageBytes + kABytes, src, kBBytes, bar_full_b + 8 * st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        uint32_t it = 0, acc_it = 0;
+        for (int w = 0; w < n_work; ++w) {
+            const BmSegment sg = p.seg[seg_begin + w];
+            for (int g = 0; g < p.n_groups; ++g, ++acc_it) {
+                mbar_wait(bar_acc_empty, (acc_it & 1) ^ 1);   // epilogue of the previous accumulator has drained TMEM
+                tc_fence_after();
+                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
+                    const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
+                    mbar_wait(bar_full_a + 8 * st, ph);
+                    mbar_wait(bar_full_b + 8 * st, ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = smem_base + st * kStageBytes, b0 = a0 + kABytes;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                            for (int k = 0; k < kChunkCols / 16; ++k) {
+                                umma_bf16(tmem_base + half * NB, umma_desc_sw128(a0 + half * 16384 + k * 32),
+                                          umma_desc_sw128(b0 + k * 32), kIdesc, (u > sg.unit_begin || k > 0) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * st);   // frees the stage once these MMAs have read it
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) umma_commit(bar_acc_full);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== A producers, then epilogue =====
+        const int pw = warp - 2;                          // 0..7
+        const int half = pw >> 2, quarter = warp & 3;     // TMEM lane quarter this warp may touch
+        const int r = half * 128 + quarter * 32 + lane;   // row inside the 256-row tile
+        uint32_t it = 0, acc_it = 0;
+        for (int w = 0; w < n_work; ++w) {
+            const BmSegment sg = p.seg[seg_begin + w];
+            for (int g = 0; g < p.n_groups; ++g, ++acc_it) {
+                unsigned long long nxt = sg.unit_begin < sg.unit_end ? p.bits[(int64_t)sg.unit_begin * kTileRows + r] : 0ull;
+                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
+                    const unsigned long long bits = nxt;
+                    if (u + 1 < sg.unit_end) nxt = p.bits[(int64_t)(u + 1) * kTileRows + r];
+                    const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
+                    mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                    uint8_t *row_ptr = gen_base + st * kStageBytes + half * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t byte = (uint32_t)(bits >> (8 * c)) & 0xFFu;
+                        uint4 v;
+                        v.x = (((byte & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+                        v.y = ((((byte >> 2) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+                        v.z = ((((byte >> 4) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+                        v.w = ((((byte >> 6) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+                        *reinterpret_cast<uint4 *>(row_ptr + ((c ^ (r & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full_a + 8 * st);
+                }
+                // ---- epilogue for (segment, group) ----
+                mbar_wait(bar_acc_full, acc_it & 1);
+                tc_fence_after();
+                const int64_t grow = (int64_t)sg.tile * kTileRows + r;
+                const bool row_ok = grow < p.n_rows;
+                const float scale = (row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f;
+                float *dst;
+                int64_t valid_cols;
+                if (sg.partial_slot < 0) {
+                    dst = p.Y + grow * p.ldy + (int64_t)g * DG;
+                    valid_cols = min((int64_t)DG, (int64_t)p.d - (int64_t)g * DG);
+                } else {
+                    dst = p.partial + (((int64_t)sg.partial_slot * p.n_groups + g) * kTileRows + r) * DG;
+                    valid_cols = DG;
+                }
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * NB;
+#pragma unroll 1
+                for (int c0 = 0; c0 < DG; c0 += 32) {
+                    uint32_t acc[S][32];
+#pragma unroll
+                    for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_row + s * DG + c0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row_ok || sg.partial_slot >= 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4) {
+                            float4 o;
+                            float *po = &o.x;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float v = __uint_as_float(acc[S - 1][q + e]);
+#pragma unroll
+                                for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
+                                po[e] = v * scale;
+                            }
+                            if (c0 + q + 4 <= valid_cols) *reinterpret_cast<float4 *>(dst + c0 + q) = o;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// fix-up: Y[tile rows] = sum over the tile's partial slots, ascending slot order (deterministic).
+template <int DG>
+__global__ void bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_groups, int32_t n_rows, int32_t d,
+                                const float *__restrict__ partial, float *__restrict__ Y, int64_t ldy) {
+    const BmFix f = fix[blockIdx.x];
+    const int g = blockIdx.y;
+    constexpr int V = DG / 4;
+    for (int idx = threadIdx.x; idx < kTileRows * V; idx += blockDim.x) {
+        const int r = idx / V, c4 = idx % V;
+        const int64_t grow = (int64_t)f.tile * kTileRows + r;
+        if (grow >= n_rows || g * DG + c4 * 4 + 4 > d) continue;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = f.slot_begin; s < f.slot_end; ++s) {
+            const float4 t = *reinterpret_cast<const float4 *>(partial + (((int64_t)s * n_groups + g) * kTileRows + r) * DG + c4 * 4);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        *reinterpret_cast<float4 *>(Y + grow * ldy + (int64_t)g * DG + c4 * 4) = a;
+    }
+}
+
+// rows of tiles that own no unit at all must still be written as zeros (TF zero-initialises its output)
+__global__ void bm_zero_tiles_kernel(const int32_t *__restrict__ tiles, int32_t n_rows, int32_t d, float *__restrict__ Y,
+                                     int64_t ldy) {
+    const int tile = tiles[blockIdx.x];
+    for (int idx = threadIdx.x; idx < kTileRows * (d / 4); idx += blockDim.x) {
+        const int r = idx / (d / 4), c4 = idx % (d / 4);
+        const int64_t grow = (int64_t)tile * kTileRows + r;
+        if (grow < n_rows) *reinterpret_cast<float4 *>(Y + grow * ldy + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// column-group width: S*DG is the UMMA N (<= 256), two accumulators of S*DG columns must fit the 512 TMEM columns
+static int dg_for(int d, int splits) { return d <= 32 ? 32 : ((d <= 64 || splits == 3) ? 64 : 128); }
+
+}  // namespace h2
+
+using namespace h2;
+
+extern "C" size_t h2_bm_host_bytes(void) { return sizeof(BmHost); }
+
+extern "C" size_t h2_bm_index_bytes(int32_t n_rows, int32_t n_cols) {
+    const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows, nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
+    // flags [nt*nc] + unit_index [nt*nc + 1] + tile_ptr [nt + 1] (all int64) + scan workspace
+    return (size_t)(2 * nt * nc + nt + 4) * 8 + h2_scan_workspace_bytes(nt * nc) + 512;
+}
+
+// Phase 1 (SYNCHRONISES): marks the non-empty 256x64 units, numbers them, returns their count.
+extern "C" int h2_bm_count(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+                           size_t index_ws_bytes, int64_t *n_units_host, h2_stream_t s) {
+    cudaStream_t st = (cudaStream_t)s;
+    H2_REQUIRE(n_rows > 0 && n_cols > 0 && rowptr && index_ws && n_units_host, H2_ERR_INVALID, "h2_bm_count: bad argument");
+    H2_REQUIRE(index_ws_bytes >= h2_bm_index_bytes(n_rows, n_cols), H2_ERR_WORKSPACE, "h2_bm_count: workspace too small");
+    const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows, nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
+    H2_REQUIRE(nt * nc < (1ll << 28), H2_ERR_UNSUPPORTED, "h2_bm_count: %lld x %lld units is too many for the bitmap format",
+               (long long)nt, (long long)nc);
+    int64_t *flags = (int64_t *)index_ws;
+    int64_t *unit_index = flags + nt * nc;
+    void *scan_ws = (void *)(unit_index + nt * nc + 1 + nt + 1 + 2);
+    H2_CUDA(cudaMemsetAsync(flags, 0, (size_t)nt * nc * 8, st));
+    bm_flag_kernel<<<(unsigned)(((int64_t)n_rows * 32 + 255) / 256), 256, 0, st>>>(n_rows, (int)nc, rowptr, col, flags);
+    H2_LAUNCHED("bm_flag_kernel");
+    int rc = h2_exclusive_scan_i64(nt * nc, flags, unit_index, scan_ws, h2_scan_workspace_bytes(nt * nc), s);
+    if (rc != H2_OK) return rc;
+    H2_CUDA(cudaMemcpyAsync(n_units_host, unit_index + nt * nc, 8, cudaMemcpyDeviceToHost, st));
+    H2_CUDA(cudaStreamSynchronize(st));
+    return H2_OK;
+}
+
+extern "C" size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n_units) {
+    const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows;
+    return align_up_sz((size_t)n_units * 4, 256) + align_up_sz((size_t)n_units * kTileRows * 8, 256) +
+           align_up_sz((size_t)(kNumSms + nt + 2) * 2 * sizeof(BmSegment), 256) + align_up_sz((size_t)(kNumSms + 2) * 4, 256) +
+           align_up_sz((size_t)(nt + 1) * sizeof(BmFix), 256) + align_up_sz((size_t)(nt + 1) * 4, 256) + 1024;
+}
+
+// Phase 2 (SYNCHRONISES): fills the bitmaps and builds the stream-K schedule (segments, partial slots, fix-ups).
+extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+                          int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, h2_stream_t s) {
+    cudaStream_t st = (cudaStream_t)s;
+    H2_REQUIRE(n_rows > 0 && n_cols > 0 && rowptr && index_ws && bm_host && bm_dev && n_units >= 0, H2_ERR_INVALID,
+               "h2_bm_fill: bad argument");
+    H2_REQUIRE(bm_dev_bytes >= h2_bm_plan_dev_bytes(n_rows, n_cols, n_units), H2_ERR_WORKSPACE, "h2_bm_fill: plan buffer too small");
+    H2_REQUIRE(n_units < 0x7fffffffLL, H2_ERR_UNSUPPORTED, "h2_bm_fill: too many units");
+    const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows, nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
+    int64_t *flags = (int64_t *)index_ws;
+    int64_t *unit_index = flags + nt * nc;
+    int64_t *tile_ptr_dev = unit_index + nt * nc + 1;
+    BmHost *h = (BmHost *)bm_host;
+    memset(h, 0, sizeof(*h));
+    h->magic = kBmMagic;
+    h->n_rows = n_rows; h->n_cols = n_cols; h->n_tiles = (int)nt; h->n_chunks = (int)nc; h->n_units = n_units;
+    size_t off = 0;
+    h->off_unit_chunk = off; off += align_up_sz((size_t)n_units * 4, 256);
+    h->off_bits = off;       off += align_up_sz((size_t)n_units * kTileRows * 8, 256);
+    h->off_seg = off;        off += align_up_sz((size_t)(kNumSms + nt + 2) * 2 * sizeof(BmSegment), 256);
+    h->off_cta_seg_ptr = off; off += align_up_sz((size_t)(kNumSms + 2) * 4, 256);
+    h->off_fix = off;        off += align_up_sz((size_t)(nt + 1) * sizeof(BmFix), 256);
+    h->off_empty_tiles = off;
+    char *base = (char *)bm_dev;
+    H2_CUDA(cudaMemsetAsync(base + h->off_bits, 0, (size_t)n_units * kTileRows * 8, st));
+    if (n_units > 0) {
+        bm_fill_kernel<<<(unsigned)(((int64_t)n_rows * 32 + 255) / 256), 256, 0, st>>>(
+            n_rows, (int)nc, rowptr, col, unit_index, (int32_t *)(base + h->off_unit_chunk),
+            (unsigned long long *)(base + h->off_bits));
+        H2_LAUNCHED("bm_fill_kernel");
+    }
+    bm_tile_ptr_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>((int)nt, (int)nc, unit_index, tile_ptr_dev);
+    H2_LAUNCHED("bm_tile_ptr_kernel");
+    std::vector<int64_t> tp(nt + 1);
+    H2_CUDA(cudaMemcpyAsync(tp.data(), tile_ptr_dev, (size_t)(nt + 1) * 8, cudaMemcpyDeviceToHost, st));
+    int64_t nnz = 0;
+    H2_CUDA(cudaMemcpyAsync(&nnz, rowptr + n_rows, 8, cudaMemcpyDeviceToHost, st));
+    H2_CUDA(cudaStreamSynchronize(st));
+    h->nnz = nnz;
+    // ---- stream-K schedule on the host: G CTAs, equal contiguous unit ranges, split at tile boundaries -------------
+    const int G = (int)std::min<int64_t>(kNumSms, std::max<int64_t>(n_units, 0));
+    std::vector<BmSegment> segs;
+    std::vector<int32_t> cta_ptr(G + 1, 0);
+    std::vector<BmFix> fixes;
+    std::vector<int32_t> empty_tiles;
+    int n_slots = 0;
+    int64_t t = 0;
+    for (int c = 0; c < G; ++c) {
+        const int64_t u0 = n_units * c / G, u1 = n_units * (c + 1) / G;
+        cta_ptr[c] = (int)segs.size();
+        int64_t u = u0;
+        while (u < u1) {
+            while (tp[t + 1] <= u) ++t;
+            const int64_t e = std::min<int64_t>(u1, tp[t + 1]);
+            const bool whole = (u == tp[t] && e == tp[t + 1]);
+            segs.push_back(BmSegment{(int32_t)t, (int32_t)u, (int32_t)e, whole ? -1 : n_slots});
+            if (!whole) {
+                if (fixes.empty() || fixes.back().tile != (int32_t)t) fixes.push_back(BmFix{(int32_t)t, n_slots, n_slots, 0});
+                fixes.back().slot_end = ++n_slots;
+            }
+            u = e;
+        }
+    }
+    cta_ptr[G] = (int)segs.size();
+    for (int64_t q = 0; q < nt; ++q)
+        if (tp[q + 1] == tp[q]) empty_tiles.push_back((int32_t)q);
+    H2_REQUIRE(segs.size() <= (size_t)(kNumSms + nt + 2) * 2, H2_ERR_UNSUPPORTED, "h2_bm_fill: segment table overflow");
+    h->n_ctas = G; h->n_partial_slots = n_slots; h->n_fix = (int)fixes.size(); h->n_empty_tiles = (int64_t)empty_tiles.size();
+    if (!segs.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_seg, segs.data(), segs.size() * sizeof(BmSegment), cudaMemcpyHostToDevice, st));
+    H2_CUDA(cudaMemcpyAsync(base + h->off_cta_seg_ptr, cta_ptr.data(), cta_ptr.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!fixes.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_fix, fixes.data(), fixes.size() * sizeof(BmFix), cudaMemcpyHostToDevice, st));
+    if (!empty_tiles.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_empty_tiles, empty_tiles.data(), empty_tiles.size() * 4, cudaMemcpyHostToDevice, st));
+    H2_CUDA(cudaStreamSynchronize(st));   // the std::vectors go out of scope
+    return H2_OK;
+}
+
+extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
+    const int dg = dg_for(d, splits);
+    const int64_t nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols, ng = (d + dg - 1) / dg;
+    return (size_t)(nc * ng * splits * dg * 128) + 256;
+}
+
+extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits) {
+    const BmHost *h = (const BmHost *)bm_host;
+    if (!h || h->magic != kBmMagic) return 0;
+    const int dg = dg_for(d, splits);
+    const int64_t ng = (d + dg - 1) / dg;
+    return (size_t)h->n_partial_slots * ng * kTileRows * dg * 4 + 256;
+}
+
+// X' = diag(dinv_col) X packed into bf16 pieces — shared by every bitmap hop of a round that uses the same dinv_col.
+extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx,
+                                const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
+    H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && (splits == 2 || splits == 3) && X && xpack && ldx >= d, H2_ERR_INVALID,
+               "h2_bm_pack_x_f32: bad argument (d=%d splits=%d)", d, splits);
+    H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
+               "h2_bm_pack_x_f32: xpack buffer too small / misaligned");
+    const int dg = dg_for(d, splits);
+    H2_REQUIRE(splits * dg <= 256, H2_ERR_UNSUPPORTED, "h2_bm_pack_x_f32: splits=%d with a %d-wide column group", splits, dg);
+    dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)((d + dg - 1) / dg));
+    cudaStream_t st = (cudaStream_t)s;
+    if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
+    else if (dg == 64) bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
+    else bm_pack_kernel<128><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
+    H2_LAUNCHED("bm_pack_kernel");
+    return H2_OK;
+}
+
+template <int DG, int S>
+static int bm_launch(const BmHost *h, const char *base, const BmParams &p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kBmStages * (kTileRows * 128 + S * DG * 128) + 1024;
+    auto kern = bm_mma_kernel<DG, S>;
+    H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<h->n_ctas, kBmThreads, smem, st>>>(p);
+    H2_LAUNCHED("bm_mma_kernel");
+    if (h->n_fix > 0) {
+        dim3 grid(h->n_fix, p.n_groups);
+        bm_fixup_kernel<DG><<<grid, 256, 0, st>>>((const BmFix *)(base + h->off_fix), p.n_groups, p.n_rows, p.d, p.partial, p.Y, p.ldy);
+        H2_LAUNCHED("bm_fixup_kernel");
+    }
+    return H2_OK;
+}
+
+// Y[:, off:off+d] = diag(dinv_row) . P . X'  for the bitmap-format pattern P (X' from h2_bm_pack_x_f32).
+extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
+                              const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
+                              size_t partial_bytes, h2_stream_t s) {
+    cudaStream_t st = (cudaStream_t)s;
+    const BmHost *h = (const BmHost *)bm_host;
+    H2_REQUIRE(h && h->magic == kBmMagic && bm_dev && xpack && Y, H2_ERR_INVALID, "h2_bm_spmm_f32: bad plan / null argument");
+    H2_REQUIRE(d > 0 && d % 4 == 0 && ldy % 4 == 0 && out_col_off % 4 == 0 && out_col_off >= 0 && out_col_off + d <= ldy &&
+               aligned16(Y) && aligned16(xpack), H2_ERR_ALIGN, "h2_bm_spmm_f32: d=%d ldy=%lld off=%lld alignment", d,
+               (long long)ldy, (long long)out_col_off);
+    H2_REQUIRE(splits == 2 || splits == 3, H2_ERR_INVALID, "h2_bm_spmm_f32: splits must be 2 or 3");
+    const int dg = dg_for(d, splits);
+    H2_REQUIRE(splits * dg <= 256, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: splits=%d with a %d-wide column group", splits, dg);
+    H2_REQUIRE(h->n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
+               H2_ERR_WORKSPACE, "h2_bm_spmm_f32: partial workspace too small");
+    const char *base = (const char *)bm_dev;
+    BmParams p;
+    p.unit_chunk = (const int32_t *)(base + h->off_unit_chunk);
+    p.bits = (const unsigned long long *)(base + h->off_bits);
+    p.seg = (const BmSegment *)(base + h->off_seg);
+    p.cta_seg_ptr = (const int32_t *)(base + h->off_cta_seg_ptr);
+    p.xpack = (const uint4 *)xpack;
+    p.dinv_row = dinv_row;
+    p.Y = Y + out_col_off;
+    p.partial = (float *)partial_ws;
+    p.ldy = ldy;
+    p.n_rows = h->n_rows; p.d = d; p.n_groups = (d + dg - 1) / dg; p.splits = splits;
+    if (h->n_empty_tiles > 0) {
+        bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, p.Y, ldy);
+        H2_LAUNCHED("bm_zero_tiles_kernel");
+    }
+    if (h->n_ctas == 0) return H2_OK;
+    if (splits == 2) {
+        if (dg == 32) return bm_launch<32, 2>(h, base, p, st);
+        if (dg == 64) return bm_launch<64, 2>(h, base, p, st);
+        return bm_launch<128, 2>(h, base, p, st);
+    }
+    if (dg == 32) return bm_launch<32, 3>(h, base, p, st);
+    if (dg == 64) return bm_launch<64, 3>(h, base, p, st);
+    set_error("h2_bm_spmm_f32: splits=3 needs column groups <= 64 wide");
+    return H2_ERR_UNSUPPORTED;
+}

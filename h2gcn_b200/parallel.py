@@ -77,7 +77,7 @@ class ShardedGraph:
     equal-rows split and all-gathered (they are also the global degree vector D2 the normalisation needs), the
     nnz-balanced boundaries are derived from them, then every rank fills and normalises its own rows."""
 
-    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None):
+    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=2):
         from . import ops
         self.rank, self.world, self.device, self.group = rank, world, device, group
         a = adj_scipy.tocsr()
@@ -109,12 +109,11 @@ class ShardedGraph:
         v2, _, d2 = ops.sym_normalize(rp2, col2, n_cols=n, row_begin=b, deg_all=deg2.contiguous())
         self.hops = [ops.SparseTensor(rp1, col1, v1, (self.n_local, n), row_begin=b, dinv=d1),
                      ops.SparseTensor(rp2, col2, v2, (self.n_local, n), row_begin=b, dinv=d2)]
-        self.plan = ops.HopPlan(self.hops, factored=factored)
+        self.plan = ops.HopPlan(self.hops, factored=factored, mode=mode, splits=splits)
         self.nnz2_local = int(col2.numel())
         self.nnz_local = int(col1.numel()) + self.nnz2_local
         self.max_row_nnz = int(max(int(deg1[b:e].max().item()) if self.n_local else 0,
                                    int(deg2[b:e].max().item()) if self.n_local else 0))
-        self.kernel_name = "fused_hops_gather_kernel (CSR gather, warp/CTA per row)"
         self._x_full = {}
 
     def gathered_input(self, x_local):

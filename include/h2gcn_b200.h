@@ -124,6 +124,33 @@ int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_dev, int32_t 
                            const h2_hop_t *hops_host, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                            h2_stream_t s);
 
+/* ---- a6 on the tensor cores: dense-ish BINARY hop patterns in "tile bitmap" format ------------------------------
+ *   For a hop whose normalised values factor as dinv_row[i] * dinv_col[j] over a 0/1 pattern
+ * (every SYM/RW-normalised nhoodSplit ring), Y = diag(dinv_row) . P . (diag(dinv_col) . X) is evaluated with
+ * tcgen05.mma: P as exact bf16 0/1 tiles expanded on the fly from 1 bit per entry, X' = diag(dinv_col) X split into
+ * `splits` (2 or 3) bf16 pieces, fp32 accumulation in TMEM.  Same call site as h2_fused_hops_spmm_f32
+ * (GCNLayer.sparse_dense_matmul, h2gcn/models/_layers.py:62-76); results agree with the fp32 CSR path to ~4e-6
+ * relative (splits = 2) — inside the 1e-4 north-star tolerance, not bit-identical.
+ *
+ * Build (once per graph, two phases like hop2): h2_bm_count SYNCHRONISES and returns the number of non-empty
+ * 256x64 units; the caller allocates h2_bm_plan_dev_bytes(); h2_bm_fill SYNCHRONISES (it builds the stream-K
+ * schedule on the host).  `index_ws` (h2_bm_index_bytes) must stay untouched between the two calls. */
+size_t h2_bm_host_bytes(void);
+size_t h2_bm_index_bytes(int32_t n_rows, int32_t n_cols);
+int h2_bm_count(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+                size_t index_ws_bytes, int64_t *n_units_host, h2_stream_t s);
+size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n_units);
+int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+               int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, h2_stream_t s);
+/* per round: pack X' once per distinct dinv_col (NULL = no column scaling), then one h2_bm_spmm_f32 per hop. */
+size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits);
+size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits);
+int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx, const float *dinv_col,
+                     void *xpack, size_t xpack_bytes, h2_stream_t s);
+int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
+                   const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
+                   size_t partial_bytes, h2_stream_t s);
+
 /* ---- a5 / a10: dense ends writing into the concat buffer ----------------------------------------------------
  * replaces SparseDense.call (+ReLU) (_layers.py:45-52, H2GCN.py:269-270): Y[:, off:off+p] = act(Xs . W + b),
  * Xs CSR [n, F] fp32 (row-major sorted COO in the reference), W [F, p] row-major. */

@@ -301,3 +301,76 @@ def test_fused_program_is_used_and_counts_launches(dev):
     assert out.shape == (2708, 7)
     emb_model = H2GCN(parse_network_setup("M64-E-R-T1-G-V-C1-MO", 7))
     assert emb_model.getEmbeddings(t.adj, t.features, t.adj_hops).shape == (2708, 64)
+
+
+# ---- a6 on the tensor cores (tile-bitmap format, tcgen05) ---------------------------------------------------------------
+def _norm_hops(dev, z):
+    from h2gcn_b200.datasets._dataset import GraphData
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    data.adj_remove_eye()
+    return data.getTensors(getAdjNormHops=["1", "2"]).adj_hops
+
+
+@pytest.mark.parametrize("name", ["tiny_path4", "tiny_rand40", "tiny_isolated", "planetoid_cora", "planetoid_citeseer"])
+@pytest.mark.parametrize("d,splits", [(4, 2), (64, 2), (100, 2), (128, 2), (256, 2), (64, 3), (128, 3)])
+def test_tensor_core_path_vs_oracle(dev, name, d, splits):
+    """mode='tensor': both hops go through the tcgen05 kernel (partial tiles, empty tiles, zero-degree rows, column
+    groups for d > 128, d not a multiple of the group).  Same 1e-4 bar as the fp32 CSR path."""
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    z = util.load_golden(name)
+    n = int(z["feat_shape"][0])
+    hops = _norm_hops(dev, z)
+    plan = HopPlan(hops, mode="tensor", splits=splits)
+    assert plan.tensor_idx == [0, 1] and not plan.csr_idx
+    x = np.random.default_rng(d + splits).standard_normal((n, d)).astype(np.float32)
+    y = torch.full((n, 2 * d), float("nan"), device=dev)
+    plan.run(torch.from_numpy(x).to(dev), y, [0, d])
+    ref = O.fused_round(util.golden_hops(z), x)
+    err = util.rel_err(y.cpu().numpy(), ref)
+    assert err <= (TOL if splits == 2 else 2e-6), err
+    deg2 = np.bincount(util.golden_hops(z)[1][0], minlength=n)
+    assert (y[:, d:].cpu().numpy()[deg2 == 0] == 0).all()
+    y2 = torch.empty_like(y)
+    plan.run(torch.from_numpy(x).to(dev), y2, [0, d])
+    assert torch.equal(y, y2), "fixed-order partial sums: bit-reproducible"
+
+
+def test_tensor_core_path_in_the_zero_copy_buffer(dev):
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    z = util.load_golden("planetoid_cora")
+    n, p = int(z["feat_shape"][0]), 64
+    plan = HopPlan(_norm_hops(dev, z), mode="tensor")
+    r0 = np.random.default_rng(0).standard_normal((n, p)).astype(np.float32)
+    buf = torch.zeros(n, 7 * p, device=dev)
+    buf[:, 4 * p:5 * p] = torch.from_numpy(r0).to(dev)
+    plan.run(buf[:, 4 * p:5 * p], buf, [5 * p, 6 * p], d=p)
+    plan.run(buf[:, 5 * p:7 * p], buf, [0, 2 * p], d=2 * p)
+    hops = util.golden_hops(z)
+    r1 = O.fused_round(hops, r0)
+    ref = np.concatenate([O.fused_round(hops, r1), r0, r1], axis=1)
+    assert util.rel_err(buf.cpu().numpy(), ref) <= TOL
+
+
+def test_auto_mode_picks_format_by_density(dev):
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.ops import HopPlan
+    from h2gcn_b200.utils import synth
+    _, cbind = _oracle()
+    n, d = 4096, 128
+    a = synth.uniform_graph(n, 60000, seed=2)
+    data = GraphData(a, sp.identity(n, dtype=np.float32, format="csr"), device=dev)
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    plan = HopPlan(t.adj_hops)                      # A1 0.7 % dense -> CSR, A2 ~19 % dense -> tensor cores
+    assert plan.csr_idx == [0] and plan.tensor_idx == [1]
+    x = synth.features(n, d, 3)
+    y = torch.empty(n, 2 * d, device=dev)
+    plan.run(torch.from_numpy(x).to(dev), y, [0, d])
+    h = t.adj_hops
+    ref = cbind.fused_round(h[0].rowptr.cpu().numpy(), h[0].col.cpu().numpy(), h[0].values.cpu().numpy(),
+                            h[1].rowptr.cpu().numpy(), h[1].col.cpu().numpy(), h[1].values.cpu().numpy(), x)
+    assert util.rel_err(y.cpu().numpy(), ref) <= TOL
+    yc = torch.empty(n, 2 * d, device=dev)
+    HopPlan(t.adj_hops, mode="csr").run(torch.from_numpy(x).to(dev), yc, [0, d])
+    assert util.rel_err(yc.cpu().numpy(), ref) <= 1e-6
