@@ -239,7 +239,8 @@ def main():
     e2e = None
     if world == 1:
         from h2gcn_b200.ops import HostGraph
-        hg = HostGraph(g.hops_host(), g.n_local, n, d_max=d)
+        hg = HostGraph(g.hops_host(), g.n_local, n, d_max=d, dinv_host=[h.dinv.cpu().numpy() for h in g.hops],
+                       row_begin=g.row_begin, mode=args.mode, splits=args.splits)
         xh = torch.from_numpy(x_full).pin_memory()
         yh = torch.empty(g.n_local, 2 * d).pin_memory()
         for _ in range(3):

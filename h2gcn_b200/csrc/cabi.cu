@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -29,12 +30,25 @@ extern "C" int64_t h2_launch_count(void) { return g_launches.load(std::memory_or
 
 // ---- host-buffer graph handle ----------------------------------------------------------------------------------
 struct h2_graph {
-    int32_t n_rows = 0, n_cols = 0, n_hops = 0, d_max = 0;
+    int32_t n_rows = 0, n_cols = 0, n_hops = 0, d_max = 0, splits = 2, row_begin = 0;
     std::vector<void *> owned;  // every cudaMalloc'ed pointer, freed in destroy
     h2_hop_t hops[H2_MAX_HOPS];
+    const float *dinv[H2_MAX_HOPS] = {};
+    // CSR subset
+    int n_csr = 0;
+    int csr_idx[H2_MAX_HOPS];
     std::vector<char> plan_host;
     void *plan_dev = nullptr;
+    // bitmap subset
+    int n_bm = 0;
+    int bm_idx[H2_MAX_HOPS];
+    std::vector<char> bm_host[H2_MAX_HOPS];
+    void *bm_dev[H2_MAX_HOPS] = {};
+    void *xpack = nullptr, *partial = nullptr;
+    size_t xpack_bytes = 0, partial_bytes = 0;
     float *x_dev = nullptr, *y_dev = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static int dev_alloc(h2_graph *g, void **p, size_t bytes) {
@@ -46,43 +60,130 @@ static int dev_alloc(h2_graph *g, void **p, size_t bytes) {
 extern "C" int h2_graph_destroy(h2_graph_t *g) {
     if (!g) return H2_OK;
     for (void *p : g->owned) cudaFree(p);
+    if (g->side) cudaStreamDestroy(g->side);
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+    if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
     return H2_OK;
 }
 
 extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
-                               const int32_t *const *col_host, const float *const *val_host, int32_t d_max,
-                               h2_graph_t **out) {
+                               const int32_t *const *col_host, const float *const *val_host,
+                               const float *const *dinv_host, int32_t row_begin, int32_t d_max, int32_t mode,
+                               int32_t splits, h2_graph_t **out) {
     H2_REQUIRE(out && n_rows >= 0 && n_cols >= 0 && n_hops >= 1 && n_hops <= H2_MAX_HOPS && d_max >= 4 && d_max % 4 == 0,
                H2_ERR_INVALID, "h2_graph_create: n_rows=%d n_cols=%d n_hops=%d d_max=%d", n_rows, n_cols, n_hops, d_max);
-    H2_REQUIRE(rowptr_host && col_host && val_host, H2_ERR_INVALID, "h2_graph_create: null argument");
+    H2_REQUIRE(rowptr_host && col_host && val_host && mode >= 0 && mode <= 2 && (splits == 2 || splits == 3) &&
+               row_begin >= 0, H2_ERR_INVALID, "h2_graph_create: null argument / bad mode");
     h2_graph *g = new h2_graph();
-    g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = d_max;
+    g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = d_max; g->splits = splits; g->row_begin = row_begin;
     int rc = H2_OK;
     auto fail = [&](int code) { h2_graph_destroy(g); return code; };
     for (int h = 0; h < n_hops; ++h) {
         if (!rowptr_host[h]) { set_error("h2_graph_create: hop %d has no rowptr", h); return fail(H2_ERR_INVALID); }
         const int64_t nnz = rowptr_host[h][n_rows] - rowptr_host[h][0];
-        void *rp = nullptr, *c = nullptr, *v = nullptr;
+        void *rp = nullptr, *c = nullptr, *v = nullptr, *dv = nullptr;
         if ((rc = dev_alloc(g, &rp, (size_t)(n_rows + 1) * 8))) return fail(rc);
         if ((rc = dev_alloc(g, &c, (size_t)nnz * 4))) return fail(rc);
-        if ((rc = dev_alloc(g, &v, (size_t)nnz * 4))) return fail(rc);
         cudaError_t e = cudaMemcpy(rp, rowptr_host[h], (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess && nnz) e = cudaMemcpy(c, col_host[h], (size_t)nnz * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && nnz) e = cudaMemcpy(v, val_host[h], (size_t)nnz * 4, cudaMemcpyHostToDevice);
+        const bool has_dinv = dinv_host && dinv_host[h];
+        if (e == cudaSuccess && has_dinv) {
+            if ((rc = dev_alloc(g, &dv, (size_t)n_cols * 4))) return fail(rc);
+            e = cudaMemcpy(dv, dinv_host[h], (size_t)n_cols * 4, cudaMemcpyHostToDevice);
+        }
+        g->dinv[h] = (const float *)dv;
+        const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
+        const bool bitmap = has_dinv && nnz > 0 && mode != 1 && (mode == 2 || (density >= 0.02 && n_rows >= 128));
+        if (!bitmap) {
+            if (!val_host[h] && nnz) { set_error("h2_graph_create: hop %d needs explicit values", h); return fail(H2_ERR_INVALID); }
+            if ((rc = dev_alloc(g, &v, (size_t)nnz * 4))) return fail(rc);
+            if (e == cudaSuccess && nnz) e = cudaMemcpy(v, val_host[h], (size_t)nnz * 4, cudaMemcpyHostToDevice);
+            g->csr_idx[g->n_csr++] = h;
+        } else {
+            g->bm_idx[g->n_bm++] = h;
+        }
         if (e != cudaSuccess) return fail(cuda_fail(e, "h2_graph_create: upload"));
         g->hops[h] = h2_hop_t{(const int64_t *)rp, (const int32_t *)c, (const float *)v, nullptr, nullptr, 0};
     }
-    g->plan_host.resize(h2_plan_host_bytes());
-    void *ws = nullptr;
-    const size_t ws_bytes = h2_plan_workspace_bytes(n_rows, n_hops);
-    if ((rc = dev_alloc(g, &g->plan_dev, h2_plan_dev_bytes(n_rows, n_hops)))) return fail(rc);
-    if ((rc = dev_alloc(g, &ws, ws_bytes))) return fail(rc);
-    if ((rc = h2_plan_build(n_rows, n_hops, g->hops, g->plan_host.data(), g->plan_dev, ws, ws_bytes, nullptr)))
-        return fail(rc);
+    if (g->n_csr) {
+        h2_hop_t sub[H2_MAX_HOPS];
+        for (int k = 0; k < g->n_csr; ++k) sub[k] = g->hops[g->csr_idx[k]];
+        g->plan_host.resize(h2_plan_host_bytes());
+        void *ws = nullptr;
+        const size_t ws_bytes = h2_plan_workspace_bytes(n_rows, g->n_csr);
+        if ((rc = dev_alloc(g, &g->plan_dev, h2_plan_dev_bytes(n_rows, g->n_csr)))) return fail(rc);
+        if ((rc = dev_alloc(g, &ws, ws_bytes))) return fail(rc);
+        if ((rc = h2_plan_build(n_rows, g->n_csr, sub, g->plan_host.data(), g->plan_dev, ws, ws_bytes, nullptr)))
+            return fail(rc);
+    }
+    for (int k = 0; k < g->n_bm; ++k) {
+        const int h = g->bm_idx[k];
+        void *iws = nullptr;
+        const size_t iws_bytes = h2_bm_index_bytes(n_rows, n_cols);
+        if ((rc = dev_alloc(g, &iws, iws_bytes))) return fail(rc);
+        int64_t n_units = 0;
+        if ((rc = h2_bm_count(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, iws_bytes, &n_units, nullptr)))
+            return fail(rc);
+        const size_t pb = h2_bm_plan_dev_bytes(n_rows, n_cols, n_units);
+        if ((rc = dev_alloc(g, &g->bm_dev[h], pb))) return fail(rc);
+        g->bm_host[h].resize(h2_bm_host_bytes());
+        if ((rc = h2_bm_fill(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, n_units, g->bm_host[h].data(),
+                             g->bm_dev[h], pb, nullptr)))
+            return fail(rc);
+        g->partial_bytes = std::max(g->partial_bytes, h2_bm_partial_bytes(g->bm_host[h].data(), d_max, splits));
+    }
+    if (g->n_bm) {
+        g->xpack_bytes = h2_bm_xpack_bytes(n_cols, d_max, splits);
+        if ((rc = dev_alloc(g, &g->xpack, g->xpack_bytes))) return fail(rc);
+        if ((rc = dev_alloc(g, &g->partial, g->partial_bytes))) return fail(rc);
+    }
+    if (g->n_bm && g->n_csr) {
+        cudaError_t e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "h2_graph_create: side stream"));
+    }
     if ((rc = dev_alloc(g, (void **)&g->x_dev, (size_t)n_cols * d_max * 4))) return fail(rc);
     if ((rc = dev_alloc(g, (void **)&g->y_dev, (size_t)n_rows * n_hops * d_max * 4))) return fail(rc);
     *out = g;
+    return H2_OK;
+}
+
+extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                              const int64_t *offsets, h2_stream_t s) {
+    cudaStream_t st = (cudaStream_t)s;
+    H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0 && d <= g->d_max, H2_ERR_INVALID,
+               "h2_graph_round: bad argument (d=%d, d_max=%d)", d, g ? g->d_max : -1);
+    int rc = H2_OK;
+    cudaStream_t csr_stream = st;
+    if (g->n_csr && g->n_bm) {   // the CSR hops overlap with the tensor-core hops on the handle's side stream
+        H2_CUDA(cudaEventRecord(g->ev_fork, st));
+        H2_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+        csr_stream = g->side;
+    }
+    if (g->n_csr) {
+        h2_hop_t sub[H2_MAX_HOPS];
+        for (int k = 0; k < g->n_csr; ++k) {
+            sub[k] = g->hops[g->csr_idx[k]];
+            sub[k].out_col_off = offsets[g->csr_idx[k]];
+        }
+        rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy,
+                                    (h2_stream_t)csr_stream);
+        if (rc != H2_OK) return rc;
+    }
+    for (int k = 0; k < g->n_bm; ++k) {
+        const int h = g->bm_idx[k];
+        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X, ldx, g->dinv[h], g->xpack, g->xpack_bytes, s);
+        if (rc != H2_OK) return rc;
+        rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
+                            offsets[h], g->partial, g->partial_bytes, s);
+        if (rc != H2_OK) return rc;
+    }
+    if (g->n_csr && g->n_bm) {
+        H2_CUDA(cudaEventRecord(g->ev_join, g->side));
+        H2_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
+    }
     return H2_OK;
 }
 
@@ -90,15 +191,11 @@ extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host
     cudaStream_t st = (cudaStream_t)s;
     H2_REQUIRE(g && x_host && y_host && d >= 4 && d % 4 == 0 && d <= g->d_max, H2_ERR_INVALID,
                "h2_graph_round_host: bad argument (d=%d, d_max=%d)", d, g ? g->d_max : -1);
-    h2_hop_t hops[H2_MAX_HOPS];
-    for (int h = 0; h < g->n_hops; ++h) {
-        hops[h] = g->hops[h];
-        hops[h].out_col_off = (int64_t)h * d;  // GCNLayer + Flatten layout: [N, H*d]
-    }
+    int64_t offsets[H2_MAX_HOPS];
+    for (int h = 0; h < g->n_hops; ++h) offsets[h] = (int64_t)h * d;  // GCNLayer + Flatten layout: [N, H*d]
     const int64_t ldy = (int64_t)g->n_hops * d;
     H2_CUDA(cudaMemcpyAsync(g->x_dev, x_host, (size_t)g->n_cols * d * 4, cudaMemcpyHostToDevice, st));
-    int rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_hops, hops, d, g->x_dev, d,
-                                    g->y_dev, ldy, s);
+    int rc = h2_graph_round(g, d, g->x_dev, d, g->y_dev, ldy, offsets, s);
     if (rc != H2_OK) return rc;
     H2_CUDA(cudaMemcpyAsync(y_host, g->y_dev, (size_t)g->n_rows * ldy * 4, cudaMemcpyDeviceToHost, st));
     H2_CUDA(cudaStreamSynchronize(st));

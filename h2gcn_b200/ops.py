@@ -355,17 +355,23 @@ def relu_slice(x, out=None, relu=True, stream=None):
 # ------------------------------------------------------------------------------------------------------------------
 class HostGraph:
     """h2_graph_*: adjacency resident on the device, X in / Y out through HOST buffers every call (bench.py e2e)."""
+    MODES = {"auto": 0, "csr": 1, "tensor": 2}
 
-    def __init__(self, hops_host, n_rows, n_cols, d_max):
-        """hops_host: list of (rowptr int64, col int32, val fp32) numpy arrays."""
+    def __init__(self, hops_host, n_rows, n_cols, d_max, dinv_host=None, row_begin=0, mode="auto", splits=2):
+        """hops_host: list of (rowptr int64, col int32, val fp32) numpy arrays; dinv_host: optional list of fp32
+        [n_cols] scale vectors (normalised binary patterns) enabling the tensor-core format."""
         import numpy as np
         self._keep = [(np.ascontiguousarray(r, dtype=np.int64), np.ascontiguousarray(c, dtype=np.int32),
                        np.ascontiguousarray(v, dtype=np.float32)) for r, c, v in hops_host]
         H = len(self._keep)
+        self._dinv = [None if dv is None else np.ascontiguousarray(dv, dtype=np.float32)
+                      for dv in (dinv_host if dinv_host is not None else [None] * H)]
         arr = lambda k: (ctypes.c_void_p * H)(*[a[k].ctypes.data for a in self._keep])
+        dv = (ctypes.c_void_p * H)(*[None if a is None else a.ctypes.data for a in self._dinv])
         self._h = ctypes.c_void_p()
         self.n_rows, self.n_cols, self.n_hops = n_rows, n_cols, H
-        check(lib().h2_graph_create(n_rows, n_cols, H, arr(0), arr(1), arr(2), d_max, ctypes.byref(self._h)))
+        check(lib().h2_graph_create(n_rows, n_cols, H, arr(0), arr(1), arr(2), dv, row_begin, d_max, self.MODES[mode],
+                                    splits, ctypes.byref(self._h)))
 
     def round(self, x_host, y_host, stream=None):
         """x_host [n_cols, d] / y_host [n_rows, H*d]: (pinned) host torch tensors or numpy arrays, fp32, contiguous."""
@@ -374,6 +380,14 @@ class HostGraph:
         yp = y_host.data_ptr() if hasattr(y_host, "data_ptr") else y_host.ctypes.data
         check(lib().h2_graph_round_host(self._h, d, xp, yp, stream_ptr(stream)))
         return y_host
+
+    def round_device(self, x, y, offsets, d=None, stream=None):
+        """Same round on device tensors (no copies, no sync)."""
+        require_cuda(x, y)
+        d = x.shape[1] if d is None else d
+        offs = (ctypes.c_int64 * self.n_hops)(*offsets)
+        check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(y), y.stride(0), offs, stream_ptr(stream)))
+        return y
 
     def close(self):
         if self._h:

@@ -165,13 +165,20 @@ int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int64_t ldx, fl
                       h2_stream_t s);
 
 /* ---- end-to-end entry points with HOST buffers (bench.py `e2e`, the call a CPU-side caller makes) ------------
- * The graph (all hops + plan) is uploaded once (h2_graph_create, like getTensors runs once per process); every
- * h2_graph_round_host call copies X host->device, runs the fused round and copies Y device->host on `s`, then
- * SYNCHRONISES.  x_host / y_host should be pinned for full PCIe speed but need not be. */
+ * The graph (all hops, in the format chosen per hop, + schedules) is uploaded once (h2_graph_create, like getTensors
+ * runs once per process); every h2_graph_round_host call copies X host->device, runs the fused round and copies
+ * Y [n_rows, n_hops*d] device->host on `s`, then SYNCHRONISES.  x_host / y_host should be pinned for full PCIe speed.
+ * dinv_host[h]: fp32 [n_cols] scale vector when hop h is a normalised BINARY pattern (val = dinv[i]*dinv[j]); it
+ * enables the tensor-core format for that hop (NULL entry / NULL array: CSR only).  row_begin: global index of local
+ * row 0.  mode: 0 = auto (bitmap for density >= 2 %), 1 = CSR everywhere, 2 = bitmap wherever dinv is given. */
 typedef struct h2_graph h2_graph_t;
 int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
-                    const int32_t *const *col_host, const float *const *val_host, int32_t d_max, h2_graph_t **out);
+                    const int32_t *const *col_host, const float *const *val_host, const float *const *dinv_host,
+                    int32_t row_begin, int32_t d_max, int32_t mode, int32_t splits, h2_graph_t **out);
 int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s);
+/* same round on DEVICE buffers (X [n_cols, d] ld=ldx; Y: hop h at column offsets[h]); enqueues, does not synchronise. */
+int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                   const int64_t *offsets_host, h2_stream_t s);
 int h2_graph_destroy(h2_graph_t *g);
 
 #ifdef __cplusplus
