@@ -12,14 +12,18 @@
 // chunk).  A persistent grid of <= 148 CTAs gets equal contiguous ranges of units ("stream-K"); a range that does
 // not cover a whole row tile writes an fp32 partial tile that a fix-up kernel adds in a fixed order (deterministic).
 //
-// Per CTA (320 threads, 1 CTA / SM, ~193 KB shared memory, all 512 TMEM columns):
+// Per CTA (320 threads, 1 CTA / SM, all 512 TMEM columns):
 //   warp 0      : TMA producer — one `cp.async.bulk` (1-D TMA, UBLKCP) per unit copies the pre-packed, pre-swizzled
-//                 32 KB X' tile [S*DG rows x 64 k] into the stage, completing on the stage's mbarrier.
+//                 X' tile [S*DG rows x 64 k] (bf16, K-major, SWIZZLE_128B image) into a stage, completing on its mbarrier.
 //   warp 1      : allocates TMEM, then a single elected thread issues 2 x 4 `tcgen05.mma.cta_group::1.kind::f16`
-//                 (M=128, N=S*DG, K=16) per unit and `tcgen05.commit`s to free the stage / publish the accumulator.
-//   warps 2..9  : A producers — thread r expands the 64 bits of row r into 64 bf16 (0.0 / 1.0) and stores them as
-//                 one 128-byte row of the K-major SWIZZLE_128B operand tile; afterwards the same warps are the
-//                 epilogue: `tcgen05.ld` 32 lanes x 32 columns, hi + lo, x dinv_row, 128-bit stores.
+//                 (M=128, N=S*DG, K=16) per unit — A operand from TENSOR MEMORY, B from shared memory — and
+//                 `tcgen05.commit`s to free the stages / publish the accumulator.
+//   warps 2..9  : A producers — thread r expands the 64 bits of row r into 64 bf16 (0.0 / 2.0: a single set bit per
+//                 element, two ALU ops per 32-bit word; the factor 2 is folded into the epilogue scale) and writes
+//                 them with ONE `tcgen05.st.32x32b.x32` into its own TMEM lane.  Keeping A out of shared memory
+//                 matters: in SS mode the UMMA operand reads (96 B/clk) plus the A and B tile writes exceeded the
+//                 128 B/clk shared-memory port (profiles/r01b).  Afterwards the same warps are the epilogue:
+//                 `tcgen05.ld` 32 lanes x 32 columns, hi + lo, x dinv_row, 128-bit stores.
 #include <cuda/ptx>
 #include <cuda_bf16.h>
 
@@ -35,7 +39,8 @@ namespace h2 {
 
 constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B tile
 constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int kBmStages = 3;
+constexpr int kAStages = 3;    // A tiles live in TMEM: 3 x (2 halves x 32 columns)
+constexpr int kBStages = 6;    // B tiles (<= 16 KB each) in shared memory
 constexpr int kBmThreads = 320;  // 10 warps
 constexpr uint32_t kBmMagic = 0x48324232u;  // "H2B2"
 
@@ -189,6 +194,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (128 lanes x 8 columns of packed bf16 pairs per K=16 step), B from shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -213,34 +228,36 @@ struct BmParams {
 template <int DG, int S>
 __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
     constexpr int NB = S * DG;                      // UMMA N
-    constexpr uint32_t kABytes = kTileRows * 128;   // 32 KB: two 128-row halves
     constexpr uint32_t kBBytes = NB * 128;
-    constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    constexpr uint32_t kTmemCols = (2 * NB <= 32) ? 32 : (2 * NB <= 64) ? 64 : (2 * NB <= 128) ? 128 : (2 * NB <= 256) ? 256 : 512;
-    static_assert(2 * NB <= 512 && NB % 16 == 0 && NB >= 16, "UMMA N / TMEM budget");
+    constexpr uint32_t kAccCols = 2 * NB;           // two 128-row halves
+    constexpr uint32_t kACol0 = kAccCols;           // A stages follow the accumulators
+    constexpr uint32_t kTmemCols = 512;
+    static_assert(kAccCols + kAStages * 64 <= 512 && NB % 16 == 0 && NB >= 16 && NB <= 256, "UMMA N / TMEM budget");
     constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: stages (1024-aligned), then barriers
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-    __shared__ uint64_t s_bar[3 * kBmStages + 2];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
+    __shared__ uint64_t s_bar[2 * kAStages + 2 * kBStages + 2];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar_full_a = smem_u32(&s_bar[0]);
-    const uint32_t bar_full_b = smem_u32(&s_bar[kBmStages]);
-    const uint32_t bar_empty = smem_u32(&s_bar[2 * kBmStages]);
-    const uint32_t bar_acc_full = smem_u32(&s_bar[3 * kBmStages]);
-    const uint32_t bar_acc_empty = smem_u32(&s_bar[3 * kBmStages + 1]);
+    const uint32_t bar_empty_a = smem_u32(&s_bar[kAStages]);
+    const uint32_t bar_full_b = smem_u32(&s_bar[2 * kAStages]);
+    const uint32_t bar_empty_b = smem_u32(&s_bar[2 * kAStages + kBStages]);
+    const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kAStages + 2 * kBStages]);
+    const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kAStages + 2 * kBStages + 1]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg_begin = p.cta_seg_ptr[blockIdx.x], seg_end = p.cta_seg_ptr[blockIdx.x + 1];
-    const int n_work = seg_end - seg_begin;  // (segment, group) pairs are enumerated group-major inside a segment
+    const int n_work = seg_end - seg_begin;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kBmStages; ++s) {
-            mbar_init(bar_full_a + 8 * s, 8);   // one arrive per A-producer warp
-            mbar_init(bar_full_b + 8 * s, 1);   // arrive.expect_tx by the TMA thread
-            mbar_init(bar_empty + 8 * s, 1);    // tcgen05.commit
+        for (int s = 0; s < kAStages; ++s) {
+            mbar_init(bar_full_a + 8 * s, 8);    // one arrive per A-producer warp
+            mbar_init(bar_empty_a + 8 * s, 1);   // tcgen05.commit
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(bar_full_b + 8 * s, 1);    // arrive.expect_tx by the TMA thread
+            mbar_init(bar_empty_b + 8 * s, 1);   // tcgen05.commit
         }
         mbar_init(bar_acc_full, 1);
         mbar_init(bar_acc_empty, 8);
@@ -264,11 +281,11 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 const BmSegment sg = p.seg[seg_begin + w];
                 for (int g = 0; g < p.n_groups; ++g) {
                     for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                        const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
-                        mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                        const uint32_t st = it % kBStages, ph = (it / kBStages) & 1;
+                        mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
                         mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes);
                         const uint4 *src = p.xpack + ((int64_t)p.unit_chunk[u] * p.n_groups + g) * (kBBytes / 16);
-                        bulk_copy_g2s(smem_base + st * kStageBytes + kABytes, src, kBBytes, bar_full_b + 8 * st);
+                        bulk_copy_g2s(smem_base + st * kBBytes, src, kBBytes, bar_full_b + 8 * st);
                     }
                 }
             }
@@ -282,21 +299,24 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 mbar_wait(bar_acc_empty, (acc_it & 1) ^ 1);   // epilogue of the previous accumulator has drained TMEM
                 tc_fence_after();
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
-                    mbar_wait(bar_full_a + 8 * st, ph);
-                    mbar_wait(bar_full_b + 8 * st, ph);
+                    const uint32_t sa = it % kAStages, pa = (it / kAStages) & 1;
+                    const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
+                    mbar_wait(bar_full_a + 8 * sa, pa);
+                    mbar_wait(bar_full_b + 8 * sb, pb);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t a0 = smem_base + st * kStageBytes, b0 = a0 + kABytes;
+                        const uint32_t b0 = smem_base + sb * kBBytes;
+                        const uint32_t a0 = tmem_base + kACol0 + sa * 64;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
 #pragma unroll
                             for (int k = 0; k < kChunkCols / 16; ++k) {
-                                umma_bf16(tmem_base + half * NB, umma_desc_sw128(a0 + half * 16384 + k * 32),
-                                          umma_desc_sw128(b0 + k * 32), kIdesc, (u > sg.unit_begin || k > 0) ? 1u : 0u);
+                                umma_bf16_ts(tmem_base + half * NB, a0 + half * 32 + k * 8, umma_desc_sw128(b0 + k * 32),
+                                             kIdesc, (u > sg.unit_begin || k > 0) ? 1u : 0u);
                             }
                         }
-                        umma_commit(bar_empty + 8 * st);   // frees the stage once these MMAs have read it
+                        umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
+                        umma_commit(bar_empty_b + 8 * sb);
                     }
                     __syncwarp();
                 }
@@ -309,6 +329,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
         const int pw = warp - 2;                          // 0..7
         const int half = pw >> 2, quarter = warp & 3;     // TMEM lane quarter this warp may touch
         const int r = half * 128 + quarter * 32 + lane;   // row inside the 256-row tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t it = 0, acc_it = 0;
         for (int w = 0; w < n_work; ++w) {
             const BmSegment sg = p.seg[seg_begin + w];
@@ -317,29 +338,30 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
                     const unsigned long long bits = nxt;
                     if (u + 1 < sg.unit_end) nxt = p.bits[(int64_t)(u + 1) * kTileRows + r];
-                    const uint32_t st = it % kBmStages, ph = (it / kBmStages) & 1;
-                    mbar_wait(bar_empty + 8 * st, ph ^ 1);
-                    uint8_t *row_ptr = gen_base + st * kStageBytes + half * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 128;
+                    // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
+                    uint32_t a[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const uint32_t byte = (uint32_t)(bits >> (8 * c)) & 0xFFu;
-                        uint4 v;
-                        v.x = (((byte & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
-                        v.y = ((((byte >> 2) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
-                        v.z = ((((byte >> 4) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
-                        v.w = ((((byte >> 6) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
-                        *reinterpret_cast<uint4 *>(row_ptr + ((c ^ (r & 7)) << 4)) = v;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            a[4 * c + i] = (byte * ((1u << (14 - 2 * i)) | (1u << (29 - 2 * i)))) & 0x40004000u;
                     }
-                    fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                    const uint32_t sa = it % kAStages, pa = (it / kAStages) & 1;
+                    mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
+                    tc_fence_after();
+                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 64 + half * 32, a);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full_a + 8 * st);
+                    if (lane == 0) mbar_arrive(bar_full_a + 8 * sa);
                 }
                 // ---- epilogue for (segment, group) ----
                 mbar_wait(bar_acc_full, acc_it & 1);
                 tc_fence_after();
                 const int64_t grow = (int64_t)sg.tile * kTileRows + r;
                 const bool row_ok = grow < p.n_rows;
-                const float scale = (row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f;
+                const float scale = 0.5f * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);   // A holds 2.0, not 1.0
                 float *dst;
                 int64_t valid_cols;
                 if (sg.partial_slot < 0) {
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     dst = p.partial + (((int64_t)sg.partial_slot * p.n_groups + g) * kTileRows + r) * DG;
                     valid_cols = DG;
                 }
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * NB;
+                const uint32_t t_row = t_lane + half * NB;
 #pragma unroll 1
                 for (int c0 = 0; c0 < DG; c0 += 32) {
                     uint32_t acc[S][32];
@@ -387,19 +409,22 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
 }
 
 // fix-up: Y[tile rows] = sum over the tile's partial slots, ascending slot order (deterministic).
+// grid = (n_fix * 8, n_groups): each CTA owns 32 rows of one tile.
 template <int DG>
-__global__ void bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_groups, int32_t n_rows, int32_t d,
-                                const float *__restrict__ partial, float *__restrict__ Y, int64_t ldy) {
-    const BmFix f = fix[blockIdx.x];
+__global__ void __launch_bounds__(256) bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_groups, int32_t n_rows,
+                                                       int32_t d, const float *__restrict__ partial,
+                                                       float *__restrict__ Y, int64_t ldy) {
+    const BmFix f = fix[blockIdx.x >> 3];
+    const int rb = (blockIdx.x & 7) * 32;
     const int g = blockIdx.y;
     constexpr int V = DG / 4;
-    for (int idx = threadIdx.x; idx < kTileRows * V; idx += blockDim.x) {
-        const int r = idx / V, c4 = idx % V;
+    for (int idx = threadIdx.x; idx < 32 * V; idx += blockDim.x) {
+        const int r = rb + idx / V, c4 = idx % V;
         const int64_t grow = (int64_t)f.tile * kTileRows + r;
         if (grow >= n_rows || g * DG + c4 * 4 + 4 > d) continue;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = f.slot_begin; s < f.slot_end; ++s) {
-            const float4 t = *reinterpret_cast<const float4 *>(partial + (((int64_t)s * n_groups + g) * kTileRows + r) * DG + c4 * 4);
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(partial + (((int64_t)s * n_groups + g) * kTileRows + r) * DG + c4 * 4));
             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         *reinterpret_cast<float4 *>(Y + grow * ldy + (int64_t)g * DG + c4 * 4) = a;
@@ -419,7 +444,7 @@ __global__ void bm_zero_tiles_kernel(const int32_t *__restrict__ tiles, int32_t 
 
 static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // column-group width: S*DG is the UMMA N (<= 256), two accumulators of S*DG columns must fit the 512 TMEM columns
-static int dg_for(int d, int splits) { return d <= 32 ? 32 : ((d <= 64 || splits == 3) ? 64 : 128); }
+static int dg_for(int d, int splits) { return (d <= 32 || splits == 3) ? 32 : 64; }
 
 }  // namespace h2
 
@@ -560,25 +585,23 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
                "h2_bm_pack_x_f32: xpack buffer too small / misaligned");
     const int dg = dg_for(d, splits);
-    H2_REQUIRE(splits * dg <= 256, H2_ERR_UNSUPPORTED, "h2_bm_pack_x_f32: splits=%d with a %d-wide column group", splits, dg);
     dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)((d + dg - 1) / dg));
     cudaStream_t st = (cudaStream_t)s;
     if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
-    else if (dg == 64) bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
-    else bm_pack_kernel<128><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
+    else bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
     H2_LAUNCHED("bm_pack_kernel");
     return H2_OK;
 }
 
 template <int DG, int S>
 static int bm_launch(const BmHost *h, const char *base, const BmParams &p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kBmStages * (kTileRows * 128 + S * DG * 128) + 1024;
+    constexpr size_t smem = (size_t)kBStages * (S * DG * 128) + 1024;
     auto kern = bm_mma_kernel<DG, S>;
     H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<h->n_ctas, kBmThreads, smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
     if (h->n_fix > 0) {
-        dim3 grid(h->n_fix, p.n_groups);
+        dim3 grid(h->n_fix * 8, p.n_groups);
         bm_fixup_kernel<DG><<<grid, 256, 0, st>>>((const BmFix *)(base + h->off_fix), p.n_groups, p.n_rows, p.d, p.partial, p.Y, p.ldy);
         H2_LAUNCHED("bm_fixup_kernel");
     }
@@ -597,7 +620,6 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
                (long long)ldy, (long long)out_col_off);
     H2_REQUIRE(splits == 2 || splits == 3, H2_ERR_INVALID, "h2_bm_spmm_f32: splits must be 2 or 3");
     const int dg = dg_for(d, splits);
-    H2_REQUIRE(splits * dg <= 256, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: splits=%d with a %d-wide column group", splits, dg);
     H2_REQUIRE(h->n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
                H2_ERR_WORKSPACE, "h2_bm_spmm_f32: partial workspace too small");
     const char *base = (const char *)bm_dev;
@@ -617,13 +639,6 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
         H2_LAUNCHED("bm_zero_tiles_kernel");
     }
     if (h->n_ctas == 0) return H2_OK;
-    if (splits == 2) {
-        if (dg == 32) return bm_launch<32, 2>(h, base, p, st);
-        if (dg == 64) return bm_launch<64, 2>(h, base, p, st);
-        return bm_launch<128, 2>(h, base, p, st);
-    }
-    if (dg == 32) return bm_launch<32, 3>(h, base, p, st);
-    if (dg == 64) return bm_launch<64, 3>(h, base, p, st);
-    set_error("h2_bm_spmm_f32: splits=3 needs column groups <= 64 wide");
-    return H2_ERR_UNSUPPORTED;
+    if (splits == 2) return dg == 32 ? bm_launch<32, 2>(h, base, p, st) : bm_launch<64, 2>(h, base, p, st);
+    return bm_launch<32, 3>(h, base, p, st);
 }
