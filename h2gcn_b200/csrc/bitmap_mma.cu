@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -39,33 +40,41 @@ namespace h2 {
 
 constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B tile
 constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int kAStages = 3;    // A tiles live in TMEM: 3 x (2 halves x 32 columns)
-constexpr int kBStages = 6;    // B tiles (<= 16 KB each) in shared memory
-constexpr int kBmThreads = 320;  // 10 warps
+constexpr int kAStages = 4;    // A tiles live in TMEM: 4 x (2 halves x 32 columns) next to 2 x 128 accumulator columns
+constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in shared memory
+constexpr int kBmThreads = 576;  // 18 warps: 2 sets of 8 A-producer/epilogue warps (0..15), TMA (16), MMA (17)
 constexpr uint32_t kBmMagic = 0x48324232u;  // "H2B2"
 
-struct BmSegment {       // one contiguous run of units inside one row tile, handled by one CTA
+struct BmSegment {       // one contiguous run of units inside one (row tile, column group), handled by one CTA
     int32_t tile;
     int32_t unit_begin;  // global unit index
     int32_t unit_end;
     int32_t partial_slot;  // -1: covers the whole tile -> write Y directly; else index into the partial workspace
+    int32_t group;         // column group (DG features) this segment computes
+    int32_t pad;
 };
 
-struct BmFix {           // one row tile whose result is the ordered sum of partial slots
+struct BmFix {           // one (row tile, column group) whose result is the ordered sum of partial slots
     int32_t tile;
     int32_t slot_begin;
     int32_t slot_end;
-    int32_t pad;
+    int32_t group;
+};
+
+constexpr int kNumScheds = 4;   // stream-K schedules for 1, 2, 4, 8 column groups (work items are group-major)
+struct BmSched {
+    int32_t n_ctas, n_partial_slots, n_fix, pad;
+    int64_t off_seg, off_cta_seg_ptr, off_fix;
 };
 
 struct BmHost {          // host header (caller's bm_host buffer)
     uint32_t magic;
     int32_t n_rows, n_cols, n_tiles, n_chunks;
-    int32_t n_ctas, n_partial_slots, n_fix;
     int64_t n_units;
     int64_t nnz;
     // offsets (bytes) into the device plan buffer
-    int64_t off_unit_chunk, off_bits, off_seg, off_cta_seg_ptr, off_fix, off_empty_tiles, n_empty_tiles;
+    int64_t off_unit_chunk, off_bits, off_empty_tiles, n_empty_tiles;
+    BmSched sched[kNumScheds];
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -155,6 +164,19 @@ __global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d,
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp, chosen by `elect.sync`: unlike `lane == 0` the compiler knows the region is
+// single-lane and emits straight-line uniform-datapath code for the UTCHMMA / UBLKCP / UTCBAR instructions in it.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync _|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -220,7 +242,7 @@ struct BmParams {
     const uint4 *xpack;          // [n_chunks][n_groups][S*DG x 64] bf16 tiles
     const float *dinv_row;       // [n_rows] (local rows) or nullptr
     float *Y;                    // + out_col_off applied by the host
-    float *partial;              // [n_partial_slots][n_groups][256][DG]
+    float *partial;              // [n_partial_slots][256][DG]
     int64_t ldy;
     int32_t n_rows, d, n_groups, splits;
 };
@@ -237,6 +259,8 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
+    const uint32_t bits_base = smem_base + kBStages * kBBytes;           // + kBStages x 2 KB unit bitmaps
+    const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_u32(smem_raw)));
     __shared__ uint64_t s_bar[2 * kAStages + 2 * kBStages + 2];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar_full_a = smem_u32(&s_bar[0]);
@@ -246,6 +270,9 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kAStages + 2 * kBStages]);
     const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kAStages + 2 * kBStages + 1]);
 
+    // The issue arbiter favours the highest warp id of a sub-partition: the MMA issuer must not queue behind the
+    // (busy-polling) producer warps, so it is the LAST warp of the CTA.
+    constexpr int kTmaWarp = 16, kMmaWarp = 17;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg_begin = p.cta_seg_ptr[blockIdx.x], seg_end = p.cta_seg_ptr[blockIdx.x + 1];
     const int n_work = seg_end - seg_begin;
@@ -260,10 +287,10 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
             mbar_init(bar_empty_b + 8 * s, 1);   // tcgen05.commit
         }
         mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 8);
+        mbar_init(bar_acc_empty, 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                      "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -273,71 +300,103 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    if (warp == 0) {
-        // ===== TMA producer (B tiles) =====
-        if (lane == 0) {
+    if (warp == kTmaWarp) {
+        // ===== TMA producer (B tiles + unit bitmaps) =====
+        if (elect_one()) {
             uint32_t it = 0;
             for (int w = 0; w < n_work; ++w) {
                 const BmSegment sg = p.seg[seg_begin + w];
-                for (int g = 0; g < p.n_groups; ++g) {
+                const int g = sg.group;
+                {
+                    int chunk_next = sg.unit_begin < sg.unit_end ? p.unit_chunk[sg.unit_begin] : 0;
                     for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
+                        const int chunk = chunk_next;
+                        if (u + 1 < sg.unit_end) chunk_next = p.unit_chunk[u + 1];   // hide the index load behind the wait
                         const uint32_t st = it % kBStages, ph = (it / kBStages) & 1;
                         mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
-                        mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes);
-                        const uint4 *src = p.xpack + ((int64_t)p.unit_chunk[u] * p.n_groups + g) * (kBBytes / 16);
+                        mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kTileRows * 8);
+                        const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
                         bulk_copy_g2s(smem_base + st * kBBytes, src, kBBytes, bar_full_b + 8 * st);
+                        bulk_copy_g2s(bits_base + st * (kTileRows * 8), p.bits + (int64_t)u * kTileRows, kTileRows * 8,
+                                      bar_full_b + 8 * st);
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        uint32_t it = 0, acc_it = 0;
-        for (int w = 0; w < n_work; ++w) {
-            const BmSegment sg = p.seg[seg_begin + w];
-            for (int g = 0; g < p.n_groups; ++g, ++acc_it) {
-                mbar_wait(bar_acc_empty, (acc_it & 1) ^ 1);   // epilogue of the previous accumulator has drained TMEM
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer: ONE elected lane runs the whole loop (no per-unit reconvergence).  A single thread executes
+        // ~one dependent instruction per 5-10 cycles, so the per-unit instruction count is what bounds the issue rate:
+        // the stage index is made a compile-time constant (8-way unrolled dispatch on `it & 7`) so every descriptor,
+        // TMEM address and barrier address is loop-invariant-base + immediate. =====
+        if (elect_one()) {
+            uint32_t it = 0, acc_it = 0;
+            auto issue_unit = [&](auto stage_c, uint32_t acc_first) {
+                constexpr uint32_t ST = decltype(stage_c)::value;      // it & 7
+                constexpr uint32_t sa = ST % kAStages, sb = ST % kBStages;
+                static_assert(8 % kAStages == 0 && 8 % kBStages == 0, "stage rings must divide the unroll factor");
+                // full_a implies full_b: the A producers read the unit's bitmap out of the same B stage
+                mbar_wait(bar_full_a + 8 * sa, (it / kAStages) & 1);
                 tc_fence_after();
-                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    const uint32_t sa = it % kAStages, pa = (it / kAStages) & 1;
-                    const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
-                    mbar_wait(bar_full_a + 8 * sa, pa);
-                    mbar_wait(bar_full_b + 8 * sb, pb);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t b0 = smem_base + sb * kBBytes;
-                        const uint32_t a0 = tmem_base + kACol0 + sa * 64;
+                const uint32_t b0 = smem_base + sb * kBBytes;
+                const uint32_t a0 = tmem_base + kACol0 + sa * 64;
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                            for (int k = 0; k < kChunkCols / 16; ++k) {
-                                umma_bf16_ts(tmem_base + half * NB, a0 + half * 32 + k * 8, umma_desc_sw128(b0 + k * 32),
-                                             kIdesc, (u > sg.unit_begin || k > 0) ? 1u : 0u);
-                            }
-                        }
-                        umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
-                        umma_commit(bar_empty_b + 8 * sb);
+                    for (int k = 0; k < kChunkCols / 16; ++k) {
+                        umma_bf16_ts(tmem_base + half * NB, a0 + half * 32 + k * 8, umma_desc_sw128(b0 + k * 32), kIdesc,
+                                     k > 0 ? 1u : acc_first);
                     }
-                    __syncwarp();
                 }
-                if (lane == 0) umma_commit(bar_acc_full);
-                __syncwarp();
+                umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
+                umma_commit(bar_empty_b + 8 * sb);
+                ++it;
+            };
+            for (int w = 0; w < n_work; ++w) {
+                const BmSegment sg = p.seg[seg_begin + w];
+                for (int once = 0; once < 1; ++once, ++acc_it) {
+                    mbar_wait(bar_acc_empty, (acc_it & 1) ^ 1);   // epilogue of the previous accumulator has drained TMEM
+                    tc_fence_after();
+                    int left = sg.unit_end - sg.unit_begin;
+                    uint32_t acc = 0;   // the first unit of a segment overwrites the accumulator
+                    while (left > 0) {
+                        switch (it & 7u) {   // falls through: consecutive units use consecutive stages
+                            case 0: issue_unit(std::integral_constant<uint32_t, 0>{}, acc); acc = 1; if (--left == 0) break;
+                            case 1: issue_unit(std::integral_constant<uint32_t, 1>{}, acc); acc = 1; if (--left == 0) break;
+                            case 2: issue_unit(std::integral_constant<uint32_t, 2>{}, acc); acc = 1; if (--left == 0) break;
+                            case 3: issue_unit(std::integral_constant<uint32_t, 3>{}, acc); acc = 1; if (--left == 0) break;
+                            case 4: issue_unit(std::integral_constant<uint32_t, 4>{}, acc); acc = 1; if (--left == 0) break;
+                            case 5: issue_unit(std::integral_constant<uint32_t, 5>{}, acc); acc = 1; if (--left == 0) break;
+                            case 6: issue_unit(std::integral_constant<uint32_t, 6>{}, acc); acc = 1; if (--left == 0) break;
+                            default: issue_unit(std::integral_constant<uint32_t, 7>{}, acc); acc = 1; --left;
+                        }
+                    }
+                    umma_commit(bar_acc_full);
+                }
             }
         }
+        __syncwarp();
     } else {
         // ===== A producers, then epilogue =====
-        const int pw = warp - 2;                          // 0..7
-        const int half = pw >> 2, quarter = warp & 3;     // TMEM lane quarter this warp may touch
+        // Two sets of 8 warps take alternate units: a warp's per-unit chain (barrier wake-up, LDS, bit expansion,
+        // tcgen05.st, wait::st, arrive) is ~1000 cycles of latency against 512 cycles of MMA work per unit, and the
+        // wait::st + arrive of a unit is deferred until just before the warp's next tcgen05.st.
+        const int pw = warp;                              // 0..15
+        const int set = pw >> 3;
+        const int half = (pw >> 2) & 1, quarter = warp & 3;   // TMEM lane quarter this warp may touch
         const int r = half * 128 + quarter * 32 + lane;   // row inside the 256-row tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t it = 0, acc_it = 0;
         for (int w = 0; w < n_work; ++w) {
             const BmSegment sg = p.seg[seg_begin + w];
-            for (int g = 0; g < p.n_groups; ++g, ++acc_it) {
-                unsigned long long nxt = sg.unit_begin < sg.unit_end ? p.bits[(int64_t)sg.unit_begin * kTileRows + r] : 0ull;
+            const int g = sg.group;
+            for (int once = 0; once < 1; ++once, ++acc_it) {
+                bool pending = false;
+                uint32_t pending_sa = 0;
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    const unsigned long long bits = nxt;
-                    if (u + 1 < sg.unit_end) nxt = p.bits[(int64_t)(u + 1) * kTileRows + r];
+                    if ((int)(it & 1) != set) continue;
+                    const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
+                    mbar_wait(bar_full_b + 8 * sb, pb);        // the unit's bitmap rides in the B stage (TMA-prefetched)
+                    const unsigned long long bits = bits_gen[sb * kTileRows + r];
                     // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
                     uint32_t a[32];
 #pragma unroll
@@ -349,14 +408,24 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     }
                     const uint32_t sa = it % kAStages, pa = (it / kAStages) & 1;
                     mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
+                    if (pending) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_full_a + 8 * pending_sa);
+                    }
                     tc_fence_after();
                     cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 64 + half * 32, a);
+                    pending = true;
+                    pending_sa = sa;
+                }
+                if (pending) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full_a + 8 * sa);
+                    if (lane == 0) mbar_arrive(bar_full_a + 8 * pending_sa);
                 }
-                // ---- epilogue for (segment, group) ----
+                // ---- epilogue for (segment, group): set s takes the 32-column blocks s, s+2, ... ----
                 mbar_wait(bar_acc_full, acc_it & 1);
                 tc_fence_after();
                 const int64_t grow = (int64_t)sg.tile * kTileRows + r;
@@ -368,12 +437,12 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     dst = p.Y + grow * p.ldy + (int64_t)g * DG;
                     valid_cols = min((int64_t)DG, (int64_t)p.d - (int64_t)g * DG);
                 } else {
-                    dst = p.partial + (((int64_t)sg.partial_slot * p.n_groups + g) * kTileRows + r) * DG;
+                    dst = p.partial + ((int64_t)sg.partial_slot * kTileRows + r) * DG;
                     valid_cols = DG;
                 }
                 const uint32_t t_row = t_lane + half * NB;
 #pragma unroll 1
-                for (int c0 = 0; c0 < DG; c0 += 32) {
+                for (int c0 = set * 32; c0 < DG; c0 += 64) {
                     uint32_t acc[S][32];
 #pragma unroll
                     for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_row + s * DG + c0);
@@ -402,21 +471,21 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
-// fix-up: Y[tile rows] = sum over the tile's partial slots, ascending slot order (deterministic).
-// grid = (n_fix * 8, n_groups): each CTA owns 32 rows of one tile.
+// fix-up: Y[tile rows, group columns] = sum over the partial slots of that (tile, group), ascending slot order
+// (deterministic).  grid = n_fix * 8: each CTA owns 32 rows.
 template <int DG>
-__global__ void __launch_bounds__(256) bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_groups, int32_t n_rows,
-                                                       int32_t d, const float *__restrict__ partial,
-                                                       float *__restrict__ Y, int64_t ldy) {
+__global__ void __launch_bounds__(256) bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_rows, int32_t d,
+                                                       const float *__restrict__ partial, float *__restrict__ Y,
+                                                       int64_t ldy) {
     const BmFix f = fix[blockIdx.x >> 3];
     const int rb = (blockIdx.x & 7) * 32;
-    const int g = blockIdx.y;
+    const int g = f.group;
     constexpr int V = DG / 4;
     for (int idx = threadIdx.x; idx < 32 * V; idx += blockDim.x) {
         const int r = rb + idx / V, c4 = idx % V;
@@ -424,7 +493,7 @@ __global__ void __launch_bounds__(256) bm_fixup_kernel(const BmFix *__restrict__
         if (grow >= n_rows || g * DG + c4 * 4 + 4 > d) continue;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = f.slot_begin; s < f.slot_end; ++s) {
-            const float4 t = __ldcs(reinterpret_cast<const float4 *>(partial + (((int64_t)s * n_groups + g) * kTileRows + r) * DG + c4 * 4));
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(partial + ((int64_t)s * kTileRows + r) * DG + c4 * 4));
             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         *reinterpret_cast<float4 *>(Y + grow * ldy + (int64_t)g * DG + c4 * 4) = a;
@@ -444,6 +513,8 @@ __global__ void bm_zero_tiles_kernel(const int32_t *__restrict__ tiles, int32_t 
 
 static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // column-group width: S*DG is the UMMA N (<= 256), two accumulators of S*DG columns must fit the 512 TMEM columns
+// column groups are rounded up to a power of two (1, 2, 4, 8): one schedule per count; padding groups compute zeros
+static int groups_for(int d, int dg) { int g = (d + dg - 1) / dg, p2 = 1; while (p2 < g) p2 <<= 1; return p2; }
 static int dg_for(int d, int splits) { return (d <= 32 || splits == 3) ? 32 : 64; }
 
 }  // namespace h2
@@ -480,11 +551,17 @@ extern "C" int h2_bm_count(int32_t n_rows, int32_t n_cols, const int64_t *rowptr
     return H2_OK;
 }
 
+static size_t sched_bytes(int64_t nt, int ng) {
+    return align_up_sz((size_t)(kNumSms + ng * (nt + 1) + 2) * sizeof(BmSegment), 256) + align_up_sz((size_t)(kNumSms + 2) * 4, 256) +
+           align_up_sz((size_t)(ng * (nt + 1)) * sizeof(BmFix), 256);
+}
+
 extern "C" size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n_units) {
     const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows;
-    return align_up_sz((size_t)n_units * 4, 256) + align_up_sz((size_t)n_units * kTileRows * 8, 256) +
-           align_up_sz((size_t)(kNumSms + nt + 2) * 2 * sizeof(BmSegment), 256) + align_up_sz((size_t)(kNumSms + 2) * 4, 256) +
-           align_up_sz((size_t)(nt + 1) * sizeof(BmFix), 256) + align_up_sz((size_t)(nt + 1) * 4, 256) + 1024;
+    size_t b = align_up_sz((size_t)n_units * 4, 256) + align_up_sz((size_t)n_units * kTileRows * 8, 256) +
+               align_up_sz((size_t)(nt + 1) * 4, 256) + 1024;
+    for (int k = 0; k < kNumScheds; ++k) b += sched_bytes(nt, 1 << k);
+    return b;
 }
 
 // Phase 2 (SYNCHRONISES): fills the bitmaps and builds the stream-K schedule (segments, partial slots, fix-ups).
@@ -506,10 +583,7 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
     size_t off = 0;
     h->off_unit_chunk = off; off += align_up_sz((size_t)n_units * 4, 256);
     h->off_bits = off;       off += align_up_sz((size_t)n_units * kTileRows * 8, 256);
-    h->off_seg = off;        off += align_up_sz((size_t)(kNumSms + nt + 2) * 2 * sizeof(BmSegment), 256);
-    h->off_cta_seg_ptr = off; off += align_up_sz((size_t)(kNumSms + 2) * 4, 256);
-    h->off_fix = off;        off += align_up_sz((size_t)(nt + 1) * sizeof(BmFix), 256);
-    h->off_empty_tiles = off;
+    h->off_empty_tiles = off; off += align_up_sz((size_t)(nt + 1) * 4, 256);
     char *base = (char *)bm_dev;
     H2_CUDA(cudaMemsetAsync(base + h->off_bits, 0, (size_t)n_units * kTileRows * 8, st));
     if (n_units > 0) {
@@ -526,46 +600,61 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
     H2_CUDA(cudaMemcpyAsync(&nnz, rowptr + n_rows, 8, cudaMemcpyDeviceToHost, st));
     H2_CUDA(cudaStreamSynchronize(st));
     h->nnz = nnz;
-    // ---- stream-K schedule on the host: G CTAs, equal contiguous unit ranges, split at tile boundaries -------------
-    const int G = (int)std::min<int64_t>(kNumSms, std::max<int64_t>(n_units, 0));
-    std::vector<BmSegment> segs;
-    std::vector<int32_t> cta_ptr(G + 1, 0);
-    std::vector<BmFix> fixes;
+    // ---- stream-K schedules on the host: for ng column groups the work items (group, unit) are linearised group-major
+    // and cut into G equal contiguous ranges; a range is split at (group, tile) boundaries into segments -------------
     std::vector<int32_t> empty_tiles;
-    int n_slots = 0;
-    int64_t t = 0;
-    for (int c = 0; c < G; ++c) {
-        const int64_t u0 = n_units * c / G, u1 = n_units * (c + 1) / G;
-        cta_ptr[c] = (int)segs.size();
-        int64_t u = u0;
-        while (u < u1) {
-            while (tp[t + 1] <= u) ++t;
-            const int64_t e = std::min<int64_t>(u1, tp[t + 1]);
-            const bool whole = (u == tp[t] && e == tp[t + 1]);
-            segs.push_back(BmSegment{(int32_t)t, (int32_t)u, (int32_t)e, whole ? -1 : n_slots});
-            if (!whole) {
-                if (fixes.empty() || fixes.back().tile != (int32_t)t) fixes.push_back(BmFix{(int32_t)t, n_slots, n_slots, 0});
-                fixes.back().slot_end = ++n_slots;
-            }
-            u = e;
-        }
-    }
-    cta_ptr[G] = (int)segs.size();
     for (int64_t q = 0; q < nt; ++q)
         if (tp[q + 1] == tp[q]) empty_tiles.push_back((int32_t)q);
-    H2_REQUIRE(segs.size() <= (size_t)(kNumSms + nt + 2) * 2, H2_ERR_UNSUPPORTED, "h2_bm_fill: segment table overflow");
-    h->n_ctas = G; h->n_partial_slots = n_slots; h->n_fix = (int)fixes.size(); h->n_empty_tiles = (int64_t)empty_tiles.size();
-    if (!segs.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_seg, segs.data(), segs.size() * sizeof(BmSegment), cudaMemcpyHostToDevice, st));
-    H2_CUDA(cudaMemcpyAsync(base + h->off_cta_seg_ptr, cta_ptr.data(), cta_ptr.size() * 4, cudaMemcpyHostToDevice, st));
-    if (!fixes.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_fix, fixes.data(), fixes.size() * sizeof(BmFix), cudaMemcpyHostToDevice, st));
+    h->n_empty_tiles = (int64_t)empty_tiles.size();
     if (!empty_tiles.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_empty_tiles, empty_tiles.data(), empty_tiles.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<BmSegment> segs[kNumScheds];
+    std::vector<int32_t> cta_ptr[kNumScheds];
+    std::vector<BmFix> fixes[kNumScheds];
+    for (int k = 0; k < kNumScheds; ++k) {
+        const int ng = 1 << k;
+        const int64_t total = n_units * ng;
+        const int G = (int)std::min<int64_t>(kNumSms, total);
+        BmSched &sc = h->sched[k];
+        cta_ptr[k].assign(G + 1, 0);
+        int n_slots = 0;
+        for (int c = 0; c < G; ++c) {
+            const int64_t q0 = total * c / G, q1 = total * (c + 1) / G;
+            cta_ptr[k][c] = (int)segs[k].size();
+            int64_t q = q0;
+            while (q < q1) {
+                const int64_t grp = q / n_units, u = q % n_units;
+                const int64_t t = (int64_t)(std::upper_bound(tp.begin(), tp.end(), u) - tp.begin()) - 1;   // tile of unit u
+                const int64_t e = std::min<int64_t>(std::min<int64_t>(tp[t + 1], n_units), u + (q1 - q));
+                const bool whole = (u == tp[t] && e == tp[t + 1]);
+                segs[k].push_back(BmSegment{(int32_t)t, (int32_t)u, (int32_t)e, whole ? -1 : n_slots, (int32_t)grp, 0});
+                if (!whole) {
+                    if (fixes[k].empty() || fixes[k].back().tile != (int32_t)t || fixes[k].back().group != (int32_t)grp)
+                        fixes[k].push_back(BmFix{(int32_t)t, n_slots, n_slots, (int32_t)grp});
+                    fixes[k].back().slot_end = ++n_slots;
+                }
+                q += e - u;
+            }
+        }
+        cta_ptr[k][G] = (int)segs[k].size();
+        H2_REQUIRE(segs[k].size() <= (size_t)(kNumSms + ng * (nt + 1) + 2) && fixes[k].size() <= (size_t)(ng * (nt + 1)),
+                   H2_ERR_UNSUPPORTED, "h2_bm_fill: schedule table overflow");
+        sc.n_ctas = G; sc.n_partial_slots = n_slots; sc.n_fix = (int)fixes[k].size();
+        sc.off_seg = off;         off += align_up_sz((size_t)(kNumSms + ng * (nt + 1) + 2) * sizeof(BmSegment), 256);
+        sc.off_cta_seg_ptr = off; off += align_up_sz((size_t)(kNumSms + 2) * 4, 256);
+        sc.off_fix = off;         off += align_up_sz((size_t)(ng * (nt + 1)) * sizeof(BmFix), 256);
+        if (!segs[k].empty()) H2_CUDA(cudaMemcpyAsync(base + sc.off_seg, segs[k].data(), segs[k].size() * sizeof(BmSegment), cudaMemcpyHostToDevice, st));
+        H2_CUDA(cudaMemcpyAsync(base + sc.off_cta_seg_ptr, cta_ptr[k].data(), cta_ptr[k].size() * 4, cudaMemcpyHostToDevice, st));
+        if (!fixes[k].empty()) H2_CUDA(cudaMemcpyAsync(base + sc.off_fix, fixes[k].data(), fixes[k].size() * sizeof(BmFix), cudaMemcpyHostToDevice, st));
+    }
     H2_CUDA(cudaStreamSynchronize(st));   // the std::vectors go out of scope
     return H2_OK;
 }
 
+static int sched_index(int n_groups) { return n_groups <= 1 ? 0 : (n_groups == 2 ? 1 : (n_groups <= 4 ? 2 : 3)); }
+
 extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
     const int dg = dg_for(d, splits);
-    const int64_t nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols, ng = (d + dg - 1) / dg;
+    const int64_t nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols, ng = groups_for(d, dg);
     return (size_t)(nc * ng * splits * dg * 128) + 256;
 }
 
@@ -573,8 +662,9 @@ extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t sp
     const BmHost *h = (const BmHost *)bm_host;
     if (!h || h->magic != kBmMagic) return 0;
     const int dg = dg_for(d, splits);
-    const int64_t ng = (d + dg - 1) / dg;
-    return (size_t)h->n_partial_slots * ng * kTileRows * dg * 4 + 256;
+    const int ng = groups_for(d, dg);
+    if (ng > 8) return 0;
+    return (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4 + 256;
 }
 
 // X' = diag(dinv_col) X packed into bf16 pieces — shared by every bitmap hop of a round that uses the same dinv_col.
@@ -585,7 +675,7 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
                "h2_bm_pack_x_f32: xpack buffer too small / misaligned");
     const int dg = dg_for(d, splits);
-    dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)((d + dg - 1) / dg));
+    dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for(d, dg));
     cudaStream_t st = (cudaStream_t)s;
     if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
     else bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
@@ -594,15 +684,14 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
 }
 
 template <int DG, int S>
-static int bm_launch(const BmHost *h, const char *base, const BmParams &p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kBStages * (S * DG * 128) + 1024;
+static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kBStages * (S * DG * 128 + kTileRows * 8) + 1024;
     auto kern = bm_mma_kernel<DG, S>;
     H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<h->n_ctas, kBmThreads, smem, st>>>(p);
+    kern<<<sc.n_ctas, kBmThreads, smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
-    if (h->n_fix > 0) {
-        dim3 grid(h->n_fix * 8, p.n_groups);
-        bm_fixup_kernel<DG><<<grid, 256, 0, st>>>((const BmFix *)(base + h->off_fix), p.n_groups, p.n_rows, p.d, p.partial, p.Y, p.ldy);
+    if (sc.n_fix > 0) {
+        bm_fixup_kernel<DG><<<sc.n_fix * 8, 256, 0, st>>>((const BmFix *)(base + sc.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
         H2_LAUNCHED("bm_fixup_kernel");
     }
     return H2_OK;
@@ -620,25 +709,28 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
                (long long)ldy, (long long)out_col_off);
     H2_REQUIRE(splits == 2 || splits == 3, H2_ERR_INVALID, "h2_bm_spmm_f32: splits must be 2 or 3");
     const int dg = dg_for(d, splits);
-    H2_REQUIRE(h->n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
+    const int n_groups = groups_for(d, dg);
+    H2_REQUIRE(n_groups <= 8, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups (max 8): split the columns", d, n_groups);
+    const BmSched &sc = h->sched[sched_index(n_groups)];
+    H2_REQUIRE(sc.n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
                H2_ERR_WORKSPACE, "h2_bm_spmm_f32: partial workspace too small");
     const char *base = (const char *)bm_dev;
     BmParams p;
     p.unit_chunk = (const int32_t *)(base + h->off_unit_chunk);
     p.bits = (const unsigned long long *)(base + h->off_bits);
-    p.seg = (const BmSegment *)(base + h->off_seg);
-    p.cta_seg_ptr = (const int32_t *)(base + h->off_cta_seg_ptr);
+    p.seg = (const BmSegment *)(base + sc.off_seg);
+    p.cta_seg_ptr = (const int32_t *)(base + sc.off_cta_seg_ptr);
     p.xpack = (const uint4 *)xpack;
     p.dinv_row = dinv_row;
     p.Y = Y + out_col_off;
     p.partial = (float *)partial_ws;
     p.ldy = ldy;
-    p.n_rows = h->n_rows; p.d = d; p.n_groups = (d + dg - 1) / dg; p.splits = splits;
+    p.n_rows = h->n_rows; p.d = d; p.n_groups = n_groups; p.splits = splits;
     if (h->n_empty_tiles > 0) {
         bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, p.Y, ldy);
         H2_LAUNCHED("bm_zero_tiles_kernel");
     }
-    if (h->n_ctas == 0) return H2_OK;
-    if (splits == 2) return dg == 32 ? bm_launch<32, 2>(h, base, p, st) : bm_launch<64, 2>(h, base, p, st);
-    return bm_launch<32, 3>(h, base, p, st);
+    if (sc.n_ctas == 0) return H2_OK;
+    if (splits == 2) return dg == 32 ? bm_launch<32, 2>(sc, base, p, st) : bm_launch<64, 2>(sc, base, p, st);
+    return bm_launch<32, 3>(sc, base, p, st);
 }
