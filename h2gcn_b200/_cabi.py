@@ -56,6 +56,9 @@ PROTOTYPES = {
     "h2_graph_create": (ctypes.c_int, [c_i32, c_i32, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                        ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_i32, c_i32, c_i32, c_i32,
                                        ctypes.POINTER(c_vp)]),
+    "h2_graph_create_device": (ctypes.c_int, [c_i32, c_i32, c_i32, ctypes.POINTER(HopDesc), ctypes.POINTER(c_i64), c_i32, c_i32,
+                                              c_i32, ctypes.POINTER(c_vp)]),
+    "h2_graph_formats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32)]),
     "h2_graph_round_host": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "h2_graph_round": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "h2_graph_destroy": (ctypes.c_int, [c_vp]),

@@ -125,37 +125,47 @@ __global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d,
     __shared__ float s_x[kChunkCols][DG + 1];
     const int chunk = blockIdx.x, g = blockIdx.y;
     const int j0 = chunk * kChunkCols, f0 = g * DG;
-    for (int idx = threadIdx.x; idx < kChunkCols * DG; idx += blockDim.x) {
-        const int k = idx / DG, f = idx % DG;
+    // coalesced 128-bit loads of the [64 x DG] slab, scaled by dinv[j]
+    constexpr int V = DG / 4;
+    for (int idx = threadIdx.x; idx < kChunkCols * V; idx += blockDim.x) {
+        const int k = idx / V, f4 = (idx % V) * 4;
         const int j = j0 + k;
-        float v = 0.f;
-        if (j < n_cols && f0 + f < d) v = X[(int64_t)j * ldx + f0 + f] * (dinv ? dinv[j] : 1.f);
-        s_x[k][f] = v;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n_cols && f0 + f4 < d) {   // d % 4 == 0: a float4 is either fully inside or fully outside
+            v = __ldg(reinterpret_cast<const float4 *>(X + (int64_t)j * ldx + f0 + f4));
+            const float sc = dinv ? __ldg(dinv + j) : 1.f;
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        }
+        s_x[k][f4] = v.x; s_x[k][f4 + 1] = v.y; s_x[k][f4 + 2] = v.z; s_x[k][f4 + 3] = v.w;
     }
     __syncthreads();
     const int n_rows_b = splits * DG;
     uint4 *tile = out + ((int64_t)chunk * n_groups + g) * (n_rows_b * 8);  // 8 x 16 B per n-row
-    for (int idx = threadIdx.x; idx < n_rows_b * 8; idx += blockDim.x) {
-        const int n = idx >> 3, c16 = idx & 7;  // 16-byte chunk c16 holds k = 8*c16 .. 8*c16+7
-        const int s = n / DG, f = n % DG;
-        uint32_t w[4];
+    // thread -> (feature f, 16-byte k-chunk c16); all `splits` pieces of an element are produced together
+    for (int idx = threadIdx.x; idx < DG * 8; idx += blockDim.x) {
+        const int f = idx >> 3, c16 = idx & 7;
+        uint32_t w[3][4];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            uint32_t h[2];
+        for (int e = 0; e < 8; ++e) {
+            float v = s_x[c16 * 8 + e][f];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float v = s_x[c16 * 8 + e + q][f];
-                __nv_bfloat16 b = __float2bfloat16_rn(v);
-                for (int t = 0; t < s; ++t) {  // residual after t pieces
+            for (int t = 0; t < 3; ++t) {
+                if (t < splits) {
+                    const __nv_bfloat16 b = __float2bfloat16_rn(v);
                     v -= __bfloat162float(b);
-                    b = __float2bfloat16_rn(v);
+                    const uint32_t h = (uint32_t)__bfloat16_as_ushort(b);
+                    if (e & 1) w[t][e >> 1] |= h << 16; else w[t][e >> 1] = h;
                 }
-                h[q] = (uint32_t)__bfloat16_as_ushort(b);
             }
-            w[e >> 1] = h[0] | (h[1] << 16);
         }
-        const int dst = (n >> 3) * 64 + (n & 7) * 8 + (c16 ^ (n & 7));  // in 16-byte units, 1024-byte atoms
-        tile[dst] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (t < splits) {
+                const int n = t * DG + f;
+                const int dst = (n >> 3) * 64 + (n & 7) * 8 + (c16 ^ (n & 7));  // in 16-byte units, 1024-byte atoms
+                tile[dst] = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+            }
+        }
     }
 }
 
@@ -478,26 +488,35 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
 }
 
 // fix-up: Y[tile rows, group columns] = sum over the partial slots of that (tile, group), ascending slot order
-// (deterministic).  grid = n_fix * 8: each CTA owns 32 rows.
+// (deterministic).  One thread per output float4; grid = (256 * DG/4 / 256, n_fix).
 template <int DG>
 __global__ void __launch_bounds__(256) bm_fixup_kernel(const BmFix *__restrict__ fix, int32_t n_rows, int32_t d,
                                                        const float *__restrict__ partial, float *__restrict__ Y,
                                                        int64_t ldy) {
-    const BmFix f = fix[blockIdx.x >> 3];
-    const int rb = (blockIdx.x & 7) * 32;
-    const int g = f.group;
+    const BmFix f = fix[blockIdx.y];
     constexpr int V = DG / 4;
-    for (int idx = threadIdx.x; idx < 32 * V; idx += blockDim.x) {
-        const int r = rb + idx / V, c4 = idx % V;
-        const int64_t grow = (int64_t)f.tile * kTileRows + r;
-        if (grow >= n_rows || g * DG + c4 * 4 + 4 > d) continue;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = f.slot_begin; s < f.slot_end; ++s) {
-            const float4 t = __ldcs(reinterpret_cast<const float4 *>(partial + ((int64_t)s * kTileRows + r) * DG + c4 * 4));
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
-        *reinterpret_cast<float4 *>(Y + grow * ldy + (int64_t)g * DG + c4 * 4) = a;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int r = idx / V, c4 = idx % V;
+    const int64_t grow = (int64_t)f.tile * kTileRows + r;
+    if (r >= kTileRows || grow >= n_rows || f.group * DG + c4 * 4 + 4 > d) return;
+    const float4 *src = reinterpret_cast<const float4 *>(partial + ((int64_t)f.slot_begin * kTileRows + r) * DG + c4 * 4);
+    constexpr int64_t kSlotStride = (int64_t)kTileRows * DG / 4;   // in float4
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = f.slot_end - f.slot_begin;
+    int s = 0;
+    for (; s + 4 <= n; s += 4) {   // 4 loads in flight, added in slot order
+        const float4 t0 = __ldcs(src + (s + 0) * kSlotStride), t1 = __ldcs(src + (s + 1) * kSlotStride);
+        const float4 t2 = __ldcs(src + (s + 2) * kSlotStride), t3 = __ldcs(src + (s + 3) * kSlotStride);
+        a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+        a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
+        a.x += t2.x; a.y += t2.y; a.z += t2.z; a.w += t2.w;
+        a.x += t3.x; a.y += t3.y; a.z += t3.z; a.w += t3.w;
     }
+    for (; s < n; ++s) {
+        const float4 t = __ldcs(src + s * kSlotStride);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    *reinterpret_cast<float4 *>(Y + grow * ldy + (int64_t)f.group * DG + c4 * 4) = a;
 }
 
 // rows of tiles that own no unit at all must still be written as zeros (TF zero-initialises its output)
@@ -691,7 +710,7 @@ static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cud
     kern<<<sc.n_ctas, kBmThreads, smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
     if (sc.n_fix > 0) {
-        bm_fixup_kernel<DG><<<sc.n_fix * 8, 256, 0, st>>>((const BmFix *)(base + sc.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
+        bm_fixup_kernel<DG><<<dim3((kTileRows * DG / 4 + 255) / 256, sc.n_fix), 256, 0, st>>>((const BmFix *)(base + sc.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
         H2_LAUNCHED("bm_fixup_kernel");
     }
     return H2_OK;

@@ -47,6 +47,7 @@ struct h2_graph {
     void *xpack = nullptr, *partial = nullptr;
     size_t xpack_bytes = 0, partial_bytes = 0;
     float *x_dev = nullptr, *y_dev = nullptr;
+    bool own_xy = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -60,11 +61,97 @@ static int dev_alloc(h2_graph *g, void **p, size_t bytes) {
 extern "C" int h2_graph_destroy(h2_graph_t *g) {
     if (!g) return H2_OK;
     for (void *p : g->owned) cudaFree(p);
+    if (g->xpack) cudaFree(g->xpack);
+    if (g->partial) cudaFree(g->partial);
+    if (g->x_dev) cudaFree(g->x_dev);
+    if (g->y_dev) cudaFree(g->y_dev);
     if (g->side) cudaStreamDestroy(g->side);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
     return H2_OK;
+}
+
+// common tail of the two constructors: formats, schedules, scratch buffers
+static int graph_finish(h2_graph *g, const bool *want_bitmap) {
+    int rc = H2_OK;
+    const int n_rows = g->n_rows, n_cols = g->n_cols;
+    for (int h = 0; h < g->n_hops; ++h) {
+        if (want_bitmap[h]) g->bm_idx[g->n_bm++] = h; else g->csr_idx[g->n_csr++] = h;
+    }
+    if (g->n_csr) {
+        h2_hop_t sub[H2_MAX_HOPS];
+        for (int k = 0; k < g->n_csr; ++k) sub[k] = g->hops[g->csr_idx[k]];
+        g->plan_host.resize(h2_plan_host_bytes());
+        void *ws = nullptr;
+        const size_t ws_bytes = h2_plan_workspace_bytes(n_rows, g->n_csr);
+        if ((rc = dev_alloc(g, &g->plan_dev, h2_plan_dev_bytes(n_rows, g->n_csr)))) return rc;
+        H2_CUDA(cudaMalloc(&ws, ws_bytes ? ws_bytes : 16));
+        rc = h2_plan_build(n_rows, g->n_csr, sub, g->plan_host.data(), g->plan_dev, ws, ws_bytes, nullptr);
+        cudaFree(ws);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < g->n_bm; ++k) {
+        const int h = g->bm_idx[k];
+        void *iws = nullptr;
+        const size_t iws_bytes = h2_bm_index_bytes(n_rows, n_cols);
+        H2_CUDA(cudaMalloc(&iws, iws_bytes));
+        int64_t n_units = 0;
+        rc = h2_bm_count(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, iws_bytes, &n_units, nullptr);
+        if (rc == H2_OK) {
+            const size_t pb = h2_bm_plan_dev_bytes(n_rows, n_cols, n_units);
+            rc = dev_alloc(g, &g->bm_dev[h], pb);
+            g->bm_host[h].resize(h2_bm_host_bytes());
+            if (rc == H2_OK)
+                rc = h2_bm_fill(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, n_units, g->bm_host[h].data(),
+                                g->bm_dev[h], pb, nullptr);
+        }
+        cudaFree(iws);
+        if (rc) return rc;
+    }
+    if (g->n_bm && g->n_csr) {
+        cudaError_t e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cuda_fail(e, "h2_graph: side stream");
+    }
+    return H2_OK;
+}
+
+// (re)allocates the per-width scratch of the tensor-core hops; called with the widest d seen so far
+static int graph_reserve(h2_graph *g, int32_t d) {
+    if (d <= g->d_max) return H2_OK;
+    int rc = H2_OK;
+    if (g->n_bm) {
+        size_t pbytes = 0;
+        for (int k = 0; k < g->n_bm; ++k)
+            pbytes = std::max(pbytes, h2_bm_partial_bytes(g->bm_host[g->bm_idx[k]].data(), d, g->splits));
+        // partial-slot counts differ per column-group count: take the max over all widths <= d that change the schedule
+        for (int dd = 4; dd < d; dd *= 2)
+            for (int k = 0; k < g->n_bm; ++k)
+                pbytes = std::max(pbytes, h2_bm_partial_bytes(g->bm_host[g->bm_idx[k]].data(), dd, g->splits));
+        g->xpack_bytes = h2_bm_xpack_bytes(g->n_cols, d, g->splits);
+        g->partial_bytes = pbytes;
+        H2_CUDA(cudaDeviceSynchronize());   // the old scratch may still be in use
+        if (g->xpack) { cudaFree(g->xpack); g->xpack = nullptr; }
+        if (g->partial) { cudaFree(g->partial); g->partial = nullptr; }
+        H2_CUDA(cudaMalloc(&g->xpack, g->xpack_bytes));
+        H2_CUDA(cudaMalloc(&g->partial, g->partial_bytes ? g->partial_bytes : 16));
+    }
+    if (g->own_xy) {
+        H2_CUDA(cudaDeviceSynchronize());
+        if (g->x_dev) { cudaFree(g->x_dev); g->x_dev = nullptr; }
+        if (g->y_dev) { cudaFree(g->y_dev); g->y_dev = nullptr; }
+        H2_CUDA(cudaMalloc((void **)&g->x_dev, (size_t)g->n_cols * d * 4 + 16));
+        H2_CUDA(cudaMalloc((void **)&g->y_dev, (size_t)g->n_rows * g->n_hops * d * 4 + 16));
+    }
+    g->d_max = d;
+    return rc;
+}
+
+static bool pick_bitmap(int32_t mode, bool has_dinv, int64_t nnz, int32_t n_rows, int32_t n_cols) {
+    const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
+    return has_dinv && nnz > 0 && mode != 1 && (mode == 2 || (density >= 0.02 && n_rows >= 128));
 }
 
 extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
@@ -76,9 +163,11 @@ extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, c
     H2_REQUIRE(rowptr_host && col_host && val_host && mode >= 0 && mode <= 2 && (splits == 2 || splits == 3) &&
                row_begin >= 0, H2_ERR_INVALID, "h2_graph_create: null argument / bad mode");
     h2_graph *g = new h2_graph();
-    g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = d_max; g->splits = splits; g->row_begin = row_begin;
+    g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = 0; g->splits = splits; g->row_begin = row_begin;
+    g->own_xy = true;
     int rc = H2_OK;
     auto fail = [&](int code) { h2_graph_destroy(g); return code; };
+    bool want_bitmap[H2_MAX_HOPS];
     for (int h = 0; h < n_hops; ++h) {
         if (!rowptr_host[h]) { set_error("h2_graph_create: hop %d has no rowptr", h); return fail(H2_ERR_INVALID); }
         const int64_t nnz = rowptr_host[h][n_rows] - rowptr_host[h][0];
@@ -93,69 +182,65 @@ extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, c
             e = cudaMemcpy(dv, dinv_host[h], (size_t)n_cols * 4, cudaMemcpyHostToDevice);
         }
         g->dinv[h] = (const float *)dv;
-        const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
-        const bool bitmap = has_dinv && nnz > 0 && mode != 1 && (mode == 2 || (density >= 0.02 && n_rows >= 128));
-        if (!bitmap) {
+        want_bitmap[h] = pick_bitmap(mode, has_dinv, nnz, n_rows, n_cols);
+        if (!want_bitmap[h]) {
             if (!val_host[h] && nnz) { set_error("h2_graph_create: hop %d needs explicit values", h); return fail(H2_ERR_INVALID); }
             if ((rc = dev_alloc(g, &v, (size_t)nnz * 4))) return fail(rc);
             if (e == cudaSuccess && nnz) e = cudaMemcpy(v, val_host[h], (size_t)nnz * 4, cudaMemcpyHostToDevice);
-            g->csr_idx[g->n_csr++] = h;
-        } else {
-            g->bm_idx[g->n_bm++] = h;
         }
         if (e != cudaSuccess) return fail(cuda_fail(e, "h2_graph_create: upload"));
         g->hops[h] = h2_hop_t{(const int64_t *)rp, (const int32_t *)c, (const float *)v, nullptr, nullptr, 0};
     }
-    if (g->n_csr) {
-        h2_hop_t sub[H2_MAX_HOPS];
-        for (int k = 0; k < g->n_csr; ++k) sub[k] = g->hops[g->csr_idx[k]];
-        g->plan_host.resize(h2_plan_host_bytes());
-        void *ws = nullptr;
-        const size_t ws_bytes = h2_plan_workspace_bytes(n_rows, g->n_csr);
-        if ((rc = dev_alloc(g, &g->plan_dev, h2_plan_dev_bytes(n_rows, g->n_csr)))) return fail(rc);
-        if ((rc = dev_alloc(g, &ws, ws_bytes))) return fail(rc);
-        if ((rc = h2_plan_build(n_rows, g->n_csr, sub, g->plan_host.data(), g->plan_dev, ws, ws_bytes, nullptr)))
-            return fail(rc);
-    }
-    for (int k = 0; k < g->n_bm; ++k) {
-        const int h = g->bm_idx[k];
-        void *iws = nullptr;
-        const size_t iws_bytes = h2_bm_index_bytes(n_rows, n_cols);
-        if ((rc = dev_alloc(g, &iws, iws_bytes))) return fail(rc);
-        int64_t n_units = 0;
-        if ((rc = h2_bm_count(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, iws_bytes, &n_units, nullptr)))
-            return fail(rc);
-        const size_t pb = h2_bm_plan_dev_bytes(n_rows, n_cols, n_units);
-        if ((rc = dev_alloc(g, &g->bm_dev[h], pb))) return fail(rc);
-        g->bm_host[h].resize(h2_bm_host_bytes());
-        if ((rc = h2_bm_fill(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, n_units, g->bm_host[h].data(),
-                             g->bm_dev[h], pb, nullptr)))
-            return fail(rc);
-        g->partial_bytes = std::max(g->partial_bytes, h2_bm_partial_bytes(g->bm_host[h].data(), d_max, splits));
-    }
-    if (g->n_bm) {
-        g->xpack_bytes = h2_bm_xpack_bytes(n_cols, d_max, splits);
-        if ((rc = dev_alloc(g, &g->xpack, g->xpack_bytes))) return fail(rc);
-        if ((rc = dev_alloc(g, &g->partial, g->partial_bytes))) return fail(rc);
-    }
-    if (g->n_bm && g->n_csr) {
-        cudaError_t e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
-        if (e != cudaSuccess) return fail(cuda_fail(e, "h2_graph_create: side stream"));
-    }
-    if ((rc = dev_alloc(g, (void **)&g->x_dev, (size_t)n_cols * d_max * 4))) return fail(rc);
-    if ((rc = dev_alloc(g, (void **)&g->y_dev, (size_t)n_rows * n_hops * d_max * 4))) return fail(rc);
+    if ((rc = graph_finish(g, want_bitmap))) return fail(rc);
+    if ((rc = graph_reserve(g, d_max))) return fail(rc);
     *out = g;
+    return H2_OK;
+}
+
+// Same handle over CSR arrays that ALREADY live on the device (no copies; the caller keeps them alive).  hops[h].val
+// may be NULL when hops[h].dinv / dinv_row are given (factored CSR); a hop with dinv can take the tensor-core format.
+extern "C" int h2_graph_create_device(int32_t n_rows, int32_t n_cols, int32_t n_hops, const h2_hop_t *hops,
+                                      const int64_t *nnz_host, int32_t row_begin, int32_t mode, int32_t splits,
+                                      h2_graph_t **out) {
+    H2_REQUIRE(out && hops && nnz_host && n_rows >= 0 && n_cols >= 0 && n_hops >= 1 && n_hops <= H2_MAX_HOPS && mode >= 0 &&
+               mode <= 2 && (splits == 2 || splits == 3) && row_begin >= 0, H2_ERR_INVALID,
+               "h2_graph_create_device: bad argument (n_hops=%d mode=%d splits=%d)", n_hops, mode, splits);
+    h2_graph *g = new h2_graph();
+    g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = 0; g->splits = splits; g->row_begin = row_begin;
+    g->own_xy = false;
+    bool want_bitmap[H2_MAX_HOPS];
+    for (int h = 0; h < n_hops; ++h) {
+        if (!hops[h].rowptr || (!hops[h].val && !hops[h].dinv)) {
+            set_error("h2_graph_create_device: hop %d needs rowptr and (val or dinv)", h);
+            h2_graph_destroy(g);
+            return H2_ERR_INVALID;
+        }
+        g->hops[h] = hops[h];
+        g->dinv[h] = hops[h].dinv;
+        want_bitmap[h] = pick_bitmap(mode, hops[h].dinv != nullptr, nnz_host[h], n_rows, n_cols);
+        if (!want_bitmap[h] && hops[h].val) { g->hops[h].dinv = nullptr; g->hops[h].dinv_row = nullptr; }
+        if (!want_bitmap[h] && !hops[h].val) g->hops[h].dinv_row = hops[h].dinv + row_begin;
+    }
+    int rc = graph_finish(g, want_bitmap);
+    if (rc) { h2_graph_destroy(g); return rc; }
+    *out = g;
+    return H2_OK;
+}
+
+// which format each hop got: fmt_out[h] = 0 (CSR) / 1 (tile bitmap)
+extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
+    H2_REQUIRE(g && fmt_out, H2_ERR_INVALID, "h2_graph_formats: null argument");
+    for (int h = 0; h < g->n_hops; ++h) fmt_out[h] = 0;
+    for (int k = 0; k < g->n_bm; ++k) fmt_out[g->bm_idx[k]] = 1;
     return H2_OK;
 }
 
 extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                               const int64_t *offsets, h2_stream_t s) {
     cudaStream_t st = (cudaStream_t)s;
-    H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0 && d <= g->d_max, H2_ERR_INVALID,
-               "h2_graph_round: bad argument (d=%d, d_max=%d)", d, g ? g->d_max : -1);
-    int rc = H2_OK;
+    H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
+    int rc = graph_reserve(g, d);
+    if (rc != H2_OK) return rc;
     cudaStream_t csr_stream = st;
     if (g->n_csr && g->n_bm) {   // the CSR hops overlap with the tensor-core hops on the handle's side stream
         H2_CUDA(cudaEventRecord(g->ev_fork, st));
@@ -189,8 +274,9 @@ extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t 
 
 extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s) {
     cudaStream_t st = (cudaStream_t)s;
-    H2_REQUIRE(g && x_host && y_host && d >= 4 && d % 4 == 0 && d <= g->d_max, H2_ERR_INVALID,
-               "h2_graph_round_host: bad argument (d=%d, d_max=%d)", d, g ? g->d_max : -1);
+    H2_REQUIRE(g && x_host && y_host && d >= 4 && d % 4 == 0 && g->own_xy, H2_ERR_INVALID,
+               "h2_graph_round_host: bad argument (d=%d) or handle created over device arrays", d);
+    { int rc0 = graph_reserve(g, d); if (rc0 != H2_OK) return rc0; }
     int64_t offsets[H2_MAX_HOPS];
     for (int h = 0; h < g->n_hops; ++h) offsets[h] = (int64_t)h * d;  // GCNLayer + Flatten layout: [N, H*d]
     const int64_t ldy = (int64_t)g->n_hops * d;

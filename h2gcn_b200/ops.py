@@ -166,66 +166,23 @@ def validate_csr(sp, stream=None):
 # ------------------------------------------------------------------------------------------------------------------
 # fused aggregation round
 # ------------------------------------------------------------------------------------------------------------------
-class BitmapHop:
-    """Tile-bitmap format (256x64 units, 1 bit per entry) of one BINARY hop pattern whose values factor as
-    dinv[i]*dinv[j] — the operand format of the tcgen05 path (csrc/bitmap_mma.cu).  Built once per graph."""
-
-    def __init__(self, sp, stream=None):
-        if sp.dinv is None:
-            raise ValueError("the tensor-core path needs SparseTensor.dinv (a normalised binary pattern)")
-        L = lib()
-        self.sp = sp
-        self.n_rows, self.n_cols = sp.n_rows, sp.dense_shape[1]
-        dev = sp.device
-        ws_bytes = L.h2_bm_index_bytes(self.n_rows, self.n_cols)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        n_units = ctypes.c_int64(0)
-        s = stream_ptr(stream)
-        check(L.h2_bm_count(self.n_rows, self.n_cols, ptr(sp.rowptr), ptr(sp.col), ptr(ws), ws_bytes,
-                            ctypes.byref(n_units), s))
-        self.n_units = int(n_units.value)
-        dev_bytes = L.h2_bm_plan_dev_bytes(self.n_rows, self.n_cols, self.n_units)
-        self._host = ctypes.create_string_buffer(L.h2_bm_host_bytes())
-        self._dev = torch.empty(dev_bytes, dtype=torch.uint8, device=dev)
-        check(L.h2_bm_fill(self.n_rows, self.n_cols, ptr(sp.rowptr), ptr(sp.col), ptr(ws), self.n_units,
-                           ctypes.addressof(self._host), ptr(self._dev), dev_bytes, s))
-        self._bufs = {}
-
-    def _buffers(self, d, splits):
-        key = (d, splits)
-        if key not in self._bufs:
-            L = lib()
-            dev = self.sp.device
-            xb = L.h2_bm_xpack_bytes(self.n_cols, d, splits)
-            pb = L.h2_bm_partial_bytes(ctypes.addressof(self._host), d, splits)
-            self._bufs[key] = (torch.empty(xb, dtype=torch.uint8, device=dev), torch.empty(max(pb, 16), dtype=torch.uint8, device=dev))
-        return self._bufs[key]
-
-    def run(self, x, out, out_col_off, d, splits=2, stream=None):
-        L = lib()
-        xpack, partial = self._buffers(d, splits)
-        s = stream_ptr(stream)
-        sp = self.sp
-        check(L.h2_bm_pack_x_f32(self.n_cols, d, splits, ptr(x), x.stride(0), ptr(sp.dinv), ptr(xpack), xpack.numel(), s))
-        check(L.h2_bm_spmm_f32(ctypes.addressof(self._host), ptr(self._dev), d, splits, ptr(xpack),
-                               sp.dinv.data_ptr() + 4 * sp.row_begin, ptr(out), out.stride(0), out_col_off,
-                               ptr(partial), partial.numel(), s))
-
-
 class HopPlan:
-    """Schedule of one fused round over a fixed list of hop adjacencies (built once per graph).
+    """One fused aggregation round over a fixed list of hop adjacencies: a thin owner of an `h2_graph_t` handle created
+    over the hops' DEVICE arrays (no copies).  Built once per graph; `run` is a single C call.
 
-    Every hop is stored in ONE of two formats, chosen from its density when the plan is built:
+    Every hop is stored in ONE of two formats, chosen by the library from its density when the plan is built:
       * CSR  -> `fused_hops_gather_kernel`, all CSR hops of the round in one launch (explicit fp32 values, or
                 `factored=True`: index-only CSR + dinv);
-      * tile bitmap -> tcgen05 kernel (`BitmapHop`), for binary patterns of density >= `tensor_density`.
+      * tile bitmap -> tcgen05 kernel (csrc/bitmap_mma.cu), for normalised BINARY patterns (SparseTensor.dinv set) of
+                density >= 2 %; CSR hops and tensor-core hops of one round overlap on two streams.
     mode: "auto" (by density), "csr" (reference-exact fp32 arithmetic everywhere), "tensor" (bitmap wherever possible).
     """
+    MODES = {"auto": 0, "csr": 1, "tensor": 2}
 
-    def __init__(self, hops, factored=False, mode="auto", splits=2, tensor_density=0.02, stream=None):
+    def __init__(self, hops, factored=False, mode="auto", splits=2, stream=None):
         if not 1 <= len(hops) <= _cabi.MAX_HOPS:
             raise ValueError(f"between 1 and {_cabi.MAX_HOPS} hops per fused round, got {len(hops)}")
-        if mode not in ("auto", "csr", "tensor"):
+        if mode not in self.MODES:
             raise ValueError(f"unknown mode {mode}")
         self.hops = list(hops)
         self.n_rows = hops[0].n_rows
@@ -235,48 +192,30 @@ class HopPlan:
                 raise ValueError("all hop adjacencies of a round must have the same shape")
             if factored and h.dinv is None:
                 raise ValueError("factored mode needs SparseTensor.dinv on every hop")
-        self.factored = factored
-        self.splits = splits
+            if h.row_begin != hops[0].row_begin:
+                raise ValueError("all hops of a round must be the same row shard")
+        self.factored, self.splits = factored, splits
         self.nnz = sum(h.nnz for h in hops)
-
-        def dense_enough(h):
-            if mode == "csr" or h.dinv is None or h.nnz == 0:
-                return False
-            if mode == "tensor":
-                return True
-            return h.nnz >= tensor_density * max(1, self.n_rows) * max(1, self.n_cols) and self.n_rows >= 128
-        self.tensor_idx = [k for k, h in enumerate(hops) if dense_enough(h)]
-        self.csr_idx = [k for k in range(len(hops)) if k not in self.tensor_idx]
-        self.bitmap = {k: BitmapHop(hops[k], stream) for k in self.tensor_idx}
-        dev = hops[0].device
-        self._desc = None
-        if self.csr_idx:
-            nc = len(self.csr_idx)
-            self._desc = (HopDesc * nc)()
-            self._fill_desc([0] * nc)
-            L = lib()
-            self._plan_host = ctypes.create_string_buffer(L.h2_plan_host_bytes())
-            self._plan_dev = torch.empty(L.h2_plan_dev_bytes(self.n_rows, nc), dtype=torch.uint8, device=dev)
-            ws_bytes = L.h2_plan_workspace_bytes(self.n_rows, nc)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            check(L.h2_plan_build(self.n_rows, nc, self._desc, ctypes.addressof(self._plan_host), ptr(self._plan_dev),
-                                  ptr(ws), ws_bytes, stream_ptr(stream)))
-        self._side = None
+        H = len(hops)
+        desc = (HopDesc * H)()
+        for k, h in enumerate(hops):
+            desc[k].rowptr, desc[k].col = ptr(h.rowptr), ptr(h.col)
+            desc[k].val = None if factored else ptr(h.values)
+            desc[k].dinv = None if (mode == "csr" and not factored) else ptr(h.dinv)
+            desc[k].dinv_row = None
+            desc[k].out_col_off = 0
+        nnz = (ctypes.c_int64 * H)(*[h.nnz for h in hops])
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(hops[0].device):
+            check(lib().h2_graph_create_device(self.n_rows, self.n_cols, H, desc, nnz, hops[0].row_begin, self.MODES[mode],
+                                               splits, ctypes.byref(self._h)))
+        fmt = (ctypes.c_int32 * H)()
+        check(lib().h2_graph_formats(self._h, fmt))
+        self.tensor_idx = [k for k in range(H) if fmt[k] == 1]
+        self.csr_idx = [k for k in range(H) if fmt[k] == 0]
         self.kernel_name = " + ".join(
             (["bm_mma_kernel (tcgen05 tile-bitmap, %d bf16 pieces) x%d" % (splits, len(self.tensor_idx))] if self.tensor_idx else []) +
             (["fused_hops_gather_kernel (CSR gather) over %d hop(s)" % len(self.csr_idx)] if self.csr_idx else []))
-
-    def _fill_desc(self, offsets):
-        for k, (hi, off) in enumerate(zip(self.csr_idx, offsets)):
-            h = self.hops[hi]
-            d = self._desc[k]
-            d.rowptr, d.col = ptr(h.rowptr), ptr(h.col)
-            if self.factored:
-                d.val, d.dinv = None, ptr(h.dinv)
-                d.dinv_row = h.dinv.data_ptr() + 4 * h.row_begin
-            else:
-                d.val, d.dinv, d.dinv_row = ptr(h.values), None, None
-            d.out_col_off = off
 
     def run(self, x, out, offsets, d=None, stream=None):
         """out[:, offsets[h] : offsets[h]+d] = hops[h] @ x[:, :d]   (x, out may be column slices of one buffer)."""
@@ -291,23 +230,24 @@ class HopPlan:
                              f"[{self.n_rows}, {self.n_cols}]")
         if len(offsets) != len(self.hops):
             raise ValueError("one output column offset per hop")
-        main = stream if stream is not None else torch.cuda.current_stream()
-        side = None
-        if self.csr_idx and self.tensor_idx:   # overlap the CSR hops with the tensor-core hops on a second stream
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=x.device)
-            side = self._side
-            side.wait_stream(main)
-        if self.csr_idx:
-            self._fill_desc([offsets[k] for k in self.csr_idx])
-            check(lib().h2_fused_hops_spmm_f32(ctypes.addressof(self._plan_host), ptr(self._plan_dev), self.n_rows,
-                                               len(self.csr_idx), self._desc, d, ptr(x), x.stride(0), ptr(out),
-                                               out.stride(0), (side or main).cuda_stream))
-        for k in self.tensor_idx:
-            self.bitmap[k].run(x, out, offsets[k], d, self.splits, main)
-        if side is not None:
-            main.wait_stream(side)
+        if d % 4 or x.stride(0) % 4 or out.stride(0) % 4 or any(o % 4 or o < 0 or o + d > out.stride(0) for o in offsets) \
+                or x.data_ptr() % 16 or out.data_ptr() % 16:
+            raise ValueError(f"fused round: d={d}, leading dimensions and column offsets must be multiples of 4 "
+                             "and the buffers 16-byte aligned")
+        offs = (ctypes.c_int64 * len(offsets))(*offsets)
+        check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(out), out.stride(0), offs, stream_ptr(stream)))
         return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().h2_graph_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def sparse_dense(feat, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None):

@@ -175,6 +175,13 @@ typedef struct h2_graph h2_graph_t;
 int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
                     const int32_t *const *col_host, const float *const *val_host, const float *const *dinv_host,
                     int32_t row_begin, int32_t d_max, int32_t mode, int32_t splits, h2_graph_t **out);
+/* Same handle over CSR arrays that ALREADY live on the device (no copies; the caller keeps them alive): this is what
+ * the Python GCNLayer / HopPlan uses, so that one fused round is ONE C call.  hops[h].val may be NULL when hops[h].dinv
+ * is given (factored CSR); hops with dinv may take the tensor-core format.  nnz_host[h] = stored entries of hop h. */
+int h2_graph_create_device(int32_t n_rows, int32_t n_cols, int32_t n_hops, const h2_hop_t *hops, const int64_t *nnz_host,
+                           int32_t row_begin, int32_t mode, int32_t splits, h2_graph_t **out);
+/* fmt_out[h] = 0 (CSR) / 1 (tile bitmap, tensor cores) */
+int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out);
 int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s);
 /* same round on DEVICE buffers (X [n_cols, d] ld=ldx; Y: hop h at column offsets[h]); enqueues, does not synchronise. */
 int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
