@@ -42,7 +42,9 @@ constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B ti
 constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kAStages = 4;    // A tiles live in TMEM: 4 x (2 halves x 32 columns) next to 2 x 128 accumulator columns
 constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in shared memory
-constexpr int kBmThreads = 576;  // 18 warps: 2 sets of 8 A-producer/epilogue warps (0..15), TMA (16), MMA (17)
+constexpr int kProducerSets = 1;  // sets of 8 A-producer/epilogue warps taking alternate units (1 keeps the register
+                                  // footprint small enough for a CSR-gather CTA of the same round to share the SM)
+constexpr int kBmThreads = (8 * kProducerSets + 2) * 32;   // producer warps, then the TMA warp, then the MMA warp (last)
 constexpr uint32_t kBmMagic = 0x48324232u;  // "H2B2"
 
 struct BmSegment {       // one contiguous run of units inside one (row tile, column group), handled by one CTA
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
 
     // The issue arbiter favours the highest warp id of a sub-partition: the MMA issuer must not queue behind the
     // (busy-polling) producer warps, so it is the LAST warp of the CTA.
-    constexpr int kTmaWarp = 16, kMmaWarp = 17;
+    constexpr int kTmaWarp = 8 * kProducerSets, kMmaWarp = 8 * kProducerSets + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg_begin = p.cta_seg_ptr[blockIdx.x], seg_end = p.cta_seg_ptr[blockIdx.x + 1];
     const int n_work = seg_end - seg_begin;
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
             mbar_init(bar_empty_b + 8 * s, 1);   // tcgen05.commit
         }
         mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 16);
+        mbar_init(bar_acc_empty, 8 * kProducerSets);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 bool pending = false;
                 uint32_t pending_sa = 0;
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    if ((int)(it & 1) != set) continue;
+                    if (kProducerSets > 1 && (int)(it % kProducerSets) != set) continue;
                     const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
                     mbar_wait(bar_full_b + 8 * sb, pb);        // the unit's bitmap rides in the B stage (TMA-prefetched)
                     const unsigned long long bits = bits_gen[sb * kTileRows + r];
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 }
                 const uint32_t t_row = t_lane + half * NB;
 #pragma unroll 1
-                for (int c0 = set * 32; c0 < DG; c0 += 64) {
+                for (int c0 = set * 32; c0 < DG; c0 += 32 * kProducerSets) {
                     uint32_t acc[S][32];
 #pragma unroll
                     for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_row + s * DG + c0);

@@ -110,7 +110,11 @@ static int graph_finish(h2_graph *g, const bool *want_bitmap) {
         if (rc) return rc;
     }
     if (g->n_bm && g->n_csr) {
-        cudaError_t e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+        // The tensor-core hops run on an internal HIGH-priority stream and the CSR hops on the caller's stream: the
+        // persistent MMA CTAs (1 per SM) are placed first and the gather CTAs fill the remaining register space.
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaError_t e = cudaStreamCreateWithPriority(&g->side, cudaStreamNonBlocking, prio_hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
         if (e != cudaSuccess) return cuda_fail(e, "h2_graph: side stream");
@@ -241,11 +245,20 @@ extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t 
     H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = graph_reserve(g, d);
     if (rc != H2_OK) return rc;
-    cudaStream_t csr_stream = st;
-    if (g->n_csr && g->n_bm) {   // the CSR hops overlap with the tensor-core hops on the handle's side stream
+    const bool two = g->n_csr && g->n_bm;
+    cudaStream_t bm_stream = st;
+    if (two) {   // fork: tensor-core hops on the high-priority stream, CSR hops stay on the caller's stream
         H2_CUDA(cudaEventRecord(g->ev_fork, st));
         H2_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
-        csr_stream = g->side;
+        bm_stream = g->side;
+    }
+    for (int k = 0; k < g->n_bm; ++k) {
+        const int h = g->bm_idx[k];
+        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X, ldx, g->dinv[h], g->xpack, g->xpack_bytes, (h2_stream_t)bm_stream);
+        if (rc != H2_OK) return rc;
+        rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
+                            offsets[h], g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
+        if (rc != H2_OK) return rc;
     }
     if (g->n_csr) {
         h2_hop_t sub[H2_MAX_HOPS];
@@ -253,19 +266,10 @@ extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t 
             sub[k] = g->hops[g->csr_idx[k]];
             sub[k].out_col_off = offsets[g->csr_idx[k]];
         }
-        rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy,
-                                    (h2_stream_t)csr_stream);
+        rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy, s);
         if (rc != H2_OK) return rc;
     }
-    for (int k = 0; k < g->n_bm; ++k) {
-        const int h = g->bm_idx[k];
-        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X, ldx, g->dinv[h], g->xpack, g->xpack_bytes, s);
-        if (rc != H2_OK) return rc;
-        rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
-                            offsets[h], g->partial, g->partial_bytes, s);
-        if (rc != H2_OK) return rc;
-    }
-    if (g->n_csr && g->n_bm) {
+    if (two) {
         H2_CUDA(cudaEventRecord(g->ev_join, g->side));
         H2_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
     }
