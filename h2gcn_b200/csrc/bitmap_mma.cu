@@ -246,6 +246,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef H2_BM_TRACE
+__device__ long long g_bm_trace[148 * 32];
+#define BM_TRACE(slot) do { if (slot < 32) g_bm_trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+#else
+#define BM_TRACE(slot) do { } while (0)
+#endif
 struct BmParams {
     const int32_t *unit_chunk;
     const unsigned long long *bits;
@@ -273,6 +279,8 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
     const uint32_t bits_base = smem_base + kBStages * kBBytes;           // + kBStages x 2 KB unit bitmaps
     const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_u32(smem_raw)));
+    constexpr int kStageStride = DG + 4;   // floats; +4 keeps 16-byte alignment and spreads rows over the banks
+    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_u32(smem_raw)) + kBStages * kTileRows * 8);
     __shared__ uint64_t s_bar[2 * kAStages + 2 * kBStages + 2];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar_full_a = smem_u32(&s_bar[0]);
@@ -290,6 +298,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     const int n_work = seg_end - seg_begin;
 
     if (threadIdx.x == 0) {
+        BM_TRACE(0);
         for (int s = 0; s < kAStages; ++s) {
             mbar_init(bar_full_a + 8 * s, 8);    // one arrive per A-producer warp
             mbar_init(bar_empty_a + 8 * s, 1);   // tcgen05.commit
@@ -366,8 +375,10 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
             for (int w = 0; w < n_work; ++w) {
                 const BmSegment sg = p.seg[seg_begin + w];
                 for (int once = 0; once < 1; ++once, ++acc_it) {
+                    BM_TRACE(2 + 6 * w);
                     mbar_wait(bar_acc_empty, (acc_it & 1) ^ 1);   // epilogue of the previous accumulator has drained TMEM
                     tc_fence_after();
+                    BM_TRACE(3 + 6 * w);
                     int left = sg.unit_end - sg.unit_begin;
                     uint32_t acc = 0;   // the first unit of a segment overwrites the accumulator
                     while (left > 0) {
@@ -383,6 +394,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                         }
                     }
                     umma_commit(bar_acc_full);
+                    BM_TRACE(4 + 6 * w);
                 }
             }
         }
@@ -438,51 +450,65 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     if (lane == 0) mbar_arrive(bar_full_a + 8 * pending_sa);
                 }
                 // ---- epilogue for (segment, group): set s takes the 32-column blocks s, s+2, ... ----
+                if (warp == 0 && lane == 0) BM_TRACE(5 + 6 * w);
                 mbar_wait(bar_acc_full, acc_it & 1);
                 tc_fence_after();
+                if (warp == 0 && lane == 0) BM_TRACE(6 + 6 * w);
                 const int64_t grow = (int64_t)sg.tile * kTileRows + r;
                 const bool row_ok = grow < p.n_rows;
                 const float scale = 0.5f * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);   // A holds 2.0, not 1.0
-                float *dst;
-                int64_t valid_cols;
-                if (sg.partial_slot < 0) {
-                    dst = p.Y + grow * p.ldy + (int64_t)g * DG;
-                    valid_cols = min((int64_t)DG, (int64_t)p.d - (int64_t)g * DG);
-                } else {
-                    dst = p.partial + ((int64_t)sg.partial_slot * kTileRows + r) * DG;
-                    valid_cols = DG;
-                }
+                const int valid_cols = sg.partial_slot < 0 ? min(DG, p.d - g * DG) : DG;
                 const uint32_t t_row = t_lane + half * NB;
+                // TMEM -> registers (lane = row) -> per-warp shared-memory stage; the accumulator is released as soon as
+                // it has been read, and the stage is then written out with fully coalesced 128-bit stores (a row of the
+                // tile is contiguous across lanes) — per-lane row stores cost one 16-byte sector write per lane.
+                float *stage = stage_gen + (warp & 7) * (32 * kStageStride);
 #pragma unroll 1
                 for (int c0 = set * 32; c0 < DG; c0 += 32 * kProducerSets) {
                     uint32_t acc[S][32];
 #pragma unroll
                     for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_row + s * DG + c0);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row_ok || sg.partial_slot >= 0) {
 #pragma unroll
-                        for (int q = 0; q < 32; q += 4) {
-                            float4 o;
-                            float *po = &o.x;
+                    for (int q = 0; q < 32; q += 4) {
+                        float4 o;
+                        float *po = &o.x;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float v = __uint_as_float(acc[S - 1][q + e]);
+                        for (int e = 0; e < 4; ++e) {
+                            float v = __uint_as_float(acc[S - 1][q + e]);
 #pragma unroll
-                                for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
-                                po[e] = v * scale;
-                            }
-                            if (c0 + q + 4 <= valid_cols) *reinterpret_cast<float4 *>(dst + c0 + q) = o;
+                            for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
+                            po[e] = v * scale;
                         }
+                        *reinterpret_cast<float4 *>(stage + lane * kStageStride + c0 + q) = o;
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty);
+                if (warp == 0 && lane == 0) BM_TRACE(7 + 6 * w);
+                if (lane == 0) mbar_arrive(bar_acc_empty);   // TMEM drained: the next segment's MMAs may start
+                {
+                    constexpr int kLanesPerRow = DG / 4, kRowsPerInstr = 32 / kLanesPerRow;
+                    const int rr = lane / kLanesPerRow, c = (lane % kLanesPerRow) * 4;
+                    const int row0 = half * 128 + quarter * 32;
+                    const bool col_ok = c + 4 <= valid_cols && (kProducerSets == 1 || (c / 32) % kProducerSets == set);
+#pragma unroll 4
+                    for (int j = 0; j < 32; j += kRowsPerInstr) {
+                        const int row = j + rr;
+                        const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + c);
+                        const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
+                        float *drow = sg.partial_slot < 0 ? p.Y + gr * p.ldy + (int64_t)g * DG
+                                                           : p.partial + ((int64_t)sg.partial_slot * kTileRows + row0 + row) * DG;
+                        if (col_ok && (sg.partial_slot >= 0 || gr < p.n_rows)) *reinterpret_cast<float4 *>(drow + c) = v;
+                    }
+                }
+                __syncwarp();   // the stage is reused by the next epilogue
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) BM_TRACE(1);
     if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -706,7 +732,7 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
 
 template <int DG, int S>
 static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kBStages * (S * DG * 128 + kTileRows * 8) + 1024;
+    constexpr size_t smem = (size_t)kBStages * (S * DG * 128 + kTileRows * 8) + 8 * 32 * (DG + 4) * 4 + 1024;
     auto kern = bm_mma_kernel<DG, S>;
     H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sc.n_ctas, kBmThreads, smem, st>>>(p);
@@ -755,3 +781,10 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     if (splits == 2) return dg == 32 ? bm_launch<32, 2>(sc, base, p, st) : bm_launch<64, 2>(sc, base, p, st);
     return bm_launch<32, 3>(sc, base, p, st);
 }
+
+#ifdef H2_BM_TRACE
+extern "C" int h2_debug_read(long long *host) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(host, h2::g_bm_trace, sizeof(long long) * 148 * 32);
+}
+#endif

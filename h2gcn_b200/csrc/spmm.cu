@@ -29,9 +29,15 @@ struct HopDev {
     int64_t out_off;
 };
 
+struct __align__(16) RowDesc {   // one schedule slot: where the virtual row's entries are, which row it is
+    int64_t begin;
+    int32_t len;
+    int32_t vrow;
+};
+
 struct RoundParams {
     HopDev hop[H2_MAX_HOPS];
-    const int32_t *perm;
+    const RowDesc *perm;   // [n_vrows] sorted by len descending; nullptr: natural order (plan-less callers)
     const float *X;
     float *Y;
     const float *bias;  // optional epilogue (sparse_dense): + bias[d], relu
@@ -60,6 +66,20 @@ __global__ void plan_keys_kernel(HopPtrs hp, int32_t n_rows, int64_t n_vrows, ui
 }
 
 // keys sorted descending: count of keys > thr = first index with key <= thr; also total and max.
+__global__ void plan_desc_kernel(HopPtrs hp, int32_t n_rows, int64_t n_vrows, const int32_t *__restrict__ vrow_sorted,
+                                 RowDesc *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_vrows) return;
+    const int v = vrow_sorted[k];
+    const int h = v / n_rows, i = v - h * n_rows;
+    const int64_t b = hp.rowptr[h][i], e = hp.rowptr[h][i + 1];
+    RowDesc d;
+    d.begin = b;
+    d.len = (int32_t)min(e - b, (int64_t)0x7fffffff);
+    d.vrow = v;
+    out[k] = d;
+}
+
 __global__ void plan_counts_kernel(const uint32_t *keys_sorted, int64_t n_vrows, uint32_t thr, HopPtrs hp,
                                    int32_t n_rows, int32_t n_hops, PlanCounts *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -152,7 +172,8 @@ __device__ __forceinline__ float4 epilogue(float4 a, float scale, const float *b
 }
 
 template <int LPR, int NV>
-__global__ void __launch_bounds__(kCtaThreads) fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
+__global__ void __launch_bounds__(kCtaThreads, NV == 1 ? 4 : (NV == 2 ? 3 : 2))
+fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     extern __shared__ float4 s_part[];  // [kWarpsPerCta][d4] partial rows of a CTA-row
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -160,11 +181,20 @@ __global__ void __launch_bounds__(kCtaThreads) fused_hops_gather_kernel(const __
     const bool cta_row = b < p.n_cta_rows;
     int64_t slot = cta_row ? b : p.n_cta_rows + (b - p.n_cta_rows) * kWarpsPerCta + warp;
     if (slot >= p.n_vrows) return;  // whole warp (only in the last warp-row CTA)
-    const int64_t v = p.perm ? (int64_t)p.perm[slot] : slot;  // perm == nullptr: natural order (plan-less callers)
+    int64_t v, s, e;
+    if (p.perm) {   // one 16-byte load instead of the perm -> rowptr chain
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(p.perm + slot));
+        s = ((int64_t)(uint32_t)raw.y << 32) | (uint32_t)raw.x;
+        e = s + raw.z;
+        v = raw.w;
+    } else {
+        v = slot;
+        s = 0; e = 0;
+    }
     const int h = (int)(v / p.n_rows);
     const int i = (int)(v - (int64_t)h * p.n_rows);
     const HopDev &hop = p.hop[h];
-    int64_t s = __ldg(hop.rowptr + i), e = __ldg(hop.rowptr + i + 1);
+    if (!p.perm) { s = __ldg(hop.rowptr + i); e = __ldg(hop.rowptr + i + 1); }
     if (cta_row) {
         int64_t seg = (e - s + kWarpsPerCta - 1) / kWarpsPerCta;
         seg = (seg + 31) & ~(int64_t)31;
@@ -249,13 +279,13 @@ extern "C" size_t h2_plan_host_bytes(void) { return sizeof(PlanHost); }
 
 extern "C" size_t h2_plan_dev_bytes(int32_t n_rows, int32_t n_hops) {
     const size_t n = (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)(n_hops > 0 ? n_hops : 0);
-    return align_up(n * sizeof(int32_t), 256) + 256;
+    return align_up(n * sizeof(RowDesc), 256) + 256;
 }
 
 extern "C" size_t h2_plan_workspace_bytes(int32_t n_rows, int32_t n_hops) {
     const size_t n = (size_t)(n_rows > 0 ? n_rows : 0) * (size_t)(n_hops > 0 ? n_hops : 0);
-    // keys x2, vrow x1 (second vrow buffer is the plan itself), counts, cub temp
-    return 3 * align_up(n * 4, 256) + 256 + cub_sort_bytes((int64_t)n);
+    // keys x2, vrow x2, counts, cub temp
+    return 4 * align_up(n * 4, 256) + 256 + cub_sort_bytes((int64_t)n);
 }
 
 extern "C" int h2_plan_build(int32_t n_rows, int32_t n_hops, const h2_hop_t *hops, void *plan_host, void *plan_dev,
@@ -287,23 +317,24 @@ extern "C" int h2_plan_build(int32_t n_rows, int32_t n_hops, const h2_hop_t *hop
     uint32_t *keys_a = (uint32_t *)w;
     uint32_t *keys_b = (uint32_t *)(w + seg);
     int32_t *vrow_a = (int32_t *)(w + 2 * seg);
-    PlanCounts *cnt = (PlanCounts *)(w + 3 * seg);
-    void *cub_tmp = w + 3 * seg + 256;
-    size_t cub_have = ws_bytes - (3 * seg + 256);
-    int32_t *perm = (int32_t *)plan_dev;
+    int32_t *vrow_b = (int32_t *)(w + 3 * seg);
+    PlanCounts *cnt = (PlanCounts *)(w + 4 * seg);
+    void *cub_tmp = w + 4 * seg + 256;
+    size_t cub_have = ws_bytes - (4 * seg + 256);
+    RowDesc *perm = (RowDesc *)plan_dev;
 
     const int tpb = 256;
     plan_keys_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(hp, n_rows, n, keys_a, vrow_a);
     H2_LAUNCHED("plan_keys_kernel");
     cub::DoubleBuffer<uint32_t> dk(keys_a, keys_b);
-    cub::DoubleBuffer<int32_t> dv(vrow_a, perm);
+    cub::DoubleBuffer<int32_t> dv(vrow_a, vrow_b);
     size_t need = 0;
     H2_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, dk, dv, (int)n, 0, 32, st));
     H2_REQUIRE(need <= cub_have, H2_ERR_WORKSPACE, "h2_plan_build: sort needs %zu bytes, have %zu", need, cub_have);
     H2_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, need, dk, dv, (int)n, 0, 32, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (dv.Current() != perm)
-        H2_CUDA(cudaMemcpyAsync(perm, dv.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    plan_desc_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(hp, n_rows, n, dv.Current(), perm);
+    H2_LAUNCHED("plan_desc_kernel");
     plan_counts_kernel<<<1, 32, 0, st>>>(dk.Current(), n, (uint32_t)ph->cta_threshold, hp, n_rows, n_hops, cnt);
     H2_LAUNCHED("plan_counts_kernel");
     PlanCounts hc;
@@ -336,7 +367,7 @@ int fill_round_params(RoundParams &p, const PlanHost *ph, const void *plan_dev, 
                    (long long)hops[h].out_col_off, d, (long long)ldy);
         p.hop[h] = HopDev{hops[h].rowptr, hops[h].col, hops[h].val, hops[h].dinv, hops[h].dinv_row, hops[h].out_col_off};
     }
-    p.perm = (const int32_t *)plan_dev;
+    p.perm = (const RowDesc *)plan_dev;
     p.X = X; p.Y = Y; p.bias = nullptr;
     p.ldx = ldx; p.ldy = ldy;
     p.n_vrows = ph->n_vrows; p.n_cta_rows = ph->n_cta_rows;

@@ -174,7 +174,7 @@ class HopPlan:
       * CSR  -> `fused_hops_gather_kernel`, all CSR hops of the round in one launch (explicit fp32 values, or
                 `factored=True`: index-only CSR + dinv);
       * tile bitmap -> tcgen05 kernel (csrc/bitmap_mma.cu), for normalised BINARY patterns (SparseTensor.dinv set) of
-                density >= 2 %; CSR hops and tensor-core hops of one round overlap on two streams.
+                density >= 1 %; CSR hops and tensor-core hops of one round overlap on two streams.
     mode: "auto" (by density), "csr" (reference-exact fp32 arithmetic everywhere), "tensor" (bitmap wherever possible).
     """
     MODES = {"auto": 0, "csr": 1, "tensor": 2}

@@ -170,7 +170,7 @@ int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int64_t ldx, fl
  * Y [n_rows, n_hops*d] device->host on `s`, then SYNCHRONISES.  x_host / y_host should be pinned for full PCIe speed.
  * dinv_host[h]: fp32 [n_cols] scale vector when hop h is a normalised BINARY pattern (val = dinv[i]*dinv[j]); it
  * enables the tensor-core format for that hop (NULL entry / NULL array: CSR only).  row_begin: global index of local
- * row 0.  mode: 0 = auto (bitmap for density >= 2 %), 1 = CSR everywhere, 2 = bitmap wherever dinv is given. */
+ * row 0.  mode: 0 = auto (bitmap for density >= 1 %), 1 = CSR everywhere, 2 = bitmap wherever dinv is given. */
 typedef struct h2_graph h2_graph_t;
 int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
                     const int32_t *const *col_host, const float *const *val_host, const float *const *dinv_host,
