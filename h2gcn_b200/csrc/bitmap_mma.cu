@@ -12,18 +12,22 @@
 // chunk).  A persistent grid of <= 148 CTAs gets equal contiguous ranges of units ("stream-K"); a range that does
 // not cover a whole row tile writes an fp32 partial tile that a fix-up kernel adds in a fixed order (deterministic).
 //
-// Per CTA (320 threads, 1 CTA / SM, all 512 TMEM columns):
-//   warp 0      : TMA producer — one `cp.async.bulk` (1-D TMA, UBLKCP) per unit copies the pre-packed, pre-swizzled
-//                 X' tile [S*DG rows x 64 k] (bf16, K-major, SWIZZLE_128B image) into a stage, completing on its mbarrier.
-//   warp 1      : allocates TMEM, then a single elected thread issues 2 x 4 `tcgen05.mma.cta_group::1.kind::f16`
-//                 (M=128, N=S*DG, K=16) per unit — A operand from TENSOR MEMORY, B from shared memory — and
-//                 `tcgen05.commit`s to free the stages / publish the accumulator.
-//   warps 2..9  : A producers — thread r expands the 64 bits of row r into 64 bf16 (0.0 / 2.0: a single set bit per
+// Per CTA (320 threads, 1 CTA / SM, all 512 TMEM columns: 2 x 128 accumulator columns + 4 A stages of 64):
+//   warps 0..7  : A producers — thread r expands the 64 bits of row r into 64 bf16 (0.0 / 2.0: a single set bit per
 //                 element, two ALU ops per 32-bit word; the factor 2 is folded into the epilogue scale) and writes
-//                 them with ONE `tcgen05.st.32x32b.x32` into its own TMEM lane.  Keeping A out of shared memory
-//                 matters: in SS mode the UMMA operand reads (96 B/clk) plus the A and B tile writes exceeded the
-//                 128 B/clk shared-memory port (profiles/r01b).  Afterwards the same warps are the epilogue:
-//                 `tcgen05.ld` 32 lanes x 32 columns, hi + lo, x dinv_row, 128-bit stores.
+//                 them with ONE `tcgen05.st.32x32b.x32` into its own TMEM lane (the wait::st + arrive of a unit is
+//                 deferred to just before the warp's next store).  Afterwards the same warps are the epilogue:
+//                 `tcgen05.ld`, hi + lo, x dinv_row, a per-warp shared-memory stage, TMEM released, coalesced stores.
+//   warp 8      : TMA producer — one elected lane; per unit two `cp.async.bulk` (1-D TMA, UBLKCP): the pre-packed,
+//                 pre-swizzled X' tile [S*DG rows x 64 k] (bf16, K-major SWIZZLE_128B image) and the unit's 2 KB
+//                 bitmap, both completing on the stage's mbarrier (8-stage ring).
+//   warp 9      : allocates TMEM; ONE elected lane (`elect.sync`) runs the whole issue loop: per unit 2 x 4
+//                 `tcgen05.mma.cta_group::1.kind::f16` (M=128, N=S*DG, K=16; A from TENSOR MEMORY, B from shared
+//                 memory), `tcgen05.commit` to free the stages / publish the accumulator.  It is the LAST warp
+//                 because the issue arbiter favours the highest warp id over the polling producer warps.
+// Work items are (column group, unit) pairs, group-major, cut into <= 148 equal contiguous ranges (stream-K); a range
+// that does not cover a whole (row tile, group) writes an fp32 partial tile and `bm_fixup_kernel` adds the partials
+// of a tile in ascending slot order (deterministic).  Measurements behind these choices: profiles/README.md.
 #include <cuda/ptx>
 #include <cuda_bf16.h>
 
