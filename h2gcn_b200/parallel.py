@@ -43,21 +43,36 @@ def all_gather_rows(x_local, x_full, bounds, group=None):
 
 
 def _uneven_all_gather(local, full, bounds, group=None):
-    """Equal shard heights -> one all-gather; otherwise one broadcast per source rank (ncclAllGather and gloo's
-    allgather both need equal sizes).  `full[bounds[q]:bounds[q+1]]` receives rank q's rows."""
+    """Equal shard heights -> ONE all-gather straight into `full`.  Uneven heights -> one all-gather of shards padded to
+    the tallest one, then a compaction copy (ncclAllGather and gloo's allgather both need equal sizes).
+    `full[bounds[q]:bounds[q+1]]` receives rank q's rows."""
     world = len(bounds) - 1
-    rank = dist.get_rank(group)
     sizes = np.diff(np.asarray(bounds))
     if np.all(sizes == sizes[0]):
         dist.all_gather_into_tensor(full, local.contiguous(), group=group)
         return
-    mine = full[int(bounds[rank]):int(bounds[rank + 1])]
-    if mine.data_ptr() != local.data_ptr():
-        mine.copy_(local)
+    hmax = int(sizes.max())
+    tail = tuple(full.shape[1:])
+    padded = torch.zeros((hmax,) + tail, dtype=full.dtype, device=full.device)
+    padded[:local.shape[0]] = local
+    gathered = torch.empty((world * hmax,) + tail, dtype=full.dtype, device=full.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
     for q in range(world):
         if sizes[q]:
-            dist.broadcast(full[int(bounds[q]):int(bounds[q + 1])], src=dist.get_global_rank(group, q) if group else q,
-                           group=group)
+            full[int(bounds[q]):int(bounds[q + 1])] = gathered[q * hmax:q * hmax + int(sizes[q])]
+
+
+def partition_rows(weights, world, tolerance=1.05):
+    """Row ranges for `world` ranks: the EQUAL split when it is balanced within `tolerance` of the ideal load (then the
+    hop-boundary exchange is a single ncclAllGather), else the nnz-balanced prefix-sum split."""
+    w = np.asarray(weights, dtype=np.int64)
+    n = len(w)
+    if n % world == 0 and n > 0:
+        eq = np.arange(world + 1, dtype=np.int64) * (n // world)
+        loads = np.add.reduceat(w, eq[:-1]) if n else np.zeros(world)
+        if loads.max() <= tolerance * max(1.0, w.sum() / world):
+            return eq
+    return balanced_row_partition(w, world)
 
 
 def all_gather_counts(local_counts, bounds, group=None):
@@ -95,7 +110,7 @@ class ShardedGraph:
         ops.check(ops.lib().h2_hop2_count(n, ops.ptr(rp), ops.ptr(col), lo, hi, ops.ptr(cnt), ops.stream_ptr()))
         deg2 = all_gather_counts(cnt, eq, group)
         # nnz-balanced contiguous partition over the stacked rows
-        self.bounds = balanced_row_partition((deg1 + deg2).cpu().numpy(), world)
+        self.bounds = partition_rows((deg1 + deg2).cpu().numpy(), world)
         self.row_begin, self.row_end = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.n_local = self.row_end - self.row_begin
         b, e = self.row_begin, self.row_end

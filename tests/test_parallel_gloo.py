@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from h2gcn_b200.parallel import all_gather_counts, all_gather_rows, balanced_row_partition
+from h2gcn_b200.parallel import all_gather_counts, all_gather_rows, balanced_row_partition, partition_rows
 from h2gcn_b200.utils import synth
 
 
@@ -26,6 +26,15 @@ def test_balanced_partition_properties():
         assert loads.max() <= w.sum() / world + w.max()
     assert list(balanced_row_partition(np.zeros(10, dtype=np.int64), 4)) == [0, 2, 5, 7, 10]
     assert list(balanced_row_partition([], 2)) == [0, 0, 0]
+
+
+def test_partition_prefers_equal_split_when_balanced():
+    w = np.full(8000, 100)
+    assert list(partition_rows(w, 8)) == [1000 * q for q in range(9)]
+    w[5] = 10 ** 6                                  # a hub row: equal split is off by far -> nnz-balanced split
+    b = partition_rows(w, 8)
+    assert b[1] < 1000 and b[-1] == 8000
+    assert list(partition_rows(np.full(10, 3), 4)) == list(balanced_row_partition(np.full(10, 3), 4))   # n % P != 0
 
 
 def _free_port():
