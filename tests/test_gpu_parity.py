@@ -376,3 +376,106 @@ def test_auto_mode_picks_format_by_density(dev):
     yc = torch.empty(n, 2 * d, device=dev)
     HopPlan(t.adj_hops, mode="csr").run(torch.from_numpy(x).to(dev), yc, [0, d])
     assert util.rel_err(yc.cpu().numpy(), ref) <= 1e-6
+
+
+# ---- larger-scale pins and property tests ---------------------------------------------------------------------------
+def test_pubmed_precompute_matches_reference_digests(dev):
+    """Pubmed (N = 19 717, nnz2 = 1 075 702): the reference's own adj_hops tensors are too big to commit, their sha256
+    digests are in tests/golden/digests.json (make_golden.py).  Rows, columns AND fp32 values must hash identically."""
+    import hashlib
+    import json
+    import os
+    from h2gcn_b200.datasets._dataset import GraphData
+    z = np.load(os.path.join(util.GOLDEN, "planetoid_pubmed_adj.npz"))
+    dig = json.load(open(os.path.join(util.GOLDEN, "digests.json")))["pubmed"]
+    n = len(z["adj_indptr"]) - 1
+    adj = sp.csr_matrix((np.ones(len(z["adj_indices"]), dtype=np.float32), z["adj_indices"], z["adj_indptr"]), shape=(n, n))
+    data = GraphData(adj, sp.identity(n, dtype=np.float32, format="csr"), device=dev)
+    data.adj_remove_eye()                                  # Pubmed has 3 self loops
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert dig["_sizes"] == {"N": n, "nnz1": t.adj_hops[0].nnz, "nnz2": t.adj_hops[1].nnz}
+    for h, hop in enumerate(t.adj_hops):
+        idx = hop.indices.cpu().numpy()
+        assert sha(idx[:, 0].astype(np.int32)) == dig[f"hop{h}_rows"]
+        assert sha(idx[:, 1].astype(np.int32)) == dig[f"hop{h}_cols"]
+        assert sha(hop.values.cpu().numpy()) == dig[f"hop{h}_vals"]
+
+
+def test_random_csr_property(dev):
+    """Random CSR patterns / widths / leading dimensions / column offsets against the oracle, both formats
+    (SURVEY.md §4 item 3): empty rows, one huge row, N not a multiple of any tile."""
+    from h2gcn_b200.datasets._dataset import TransformSPAdj
+    from h2gcn_b200.ops import HopPlan, SparseTensor
+    O, _ = _oracle()
+    TransformSPAdj.device = dev
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        n = int(rng.integers(130, 900))
+        dens = float(rng.choice([0.002, 0.01, 0.05, 0.3]))
+        m = sp.random(n, n, density=dens, random_state=np.random.RandomState(trial), dtype=np.float32).tocsr()
+        m.data[:] = 1.0
+        m = m.tolil()
+        m[int(rng.integers(0, n)), :] = 1.0                 # one full row
+        m[int(rng.integers(0, n)), :] = 0.0                 # one empty row
+        m = m.tocsr()
+        m.eliminate_zeros()
+        hop = TransformSPAdj.normalize(m, TransformSPAdj.NType.SYM_NORMALIZED)     # binary pattern -> dinv factorisation
+        d = int(rng.choice([4, 8, 20, 36, 64, 100, 132, 256]))
+        ld_x, ld_y = d + 4 * int(rng.integers(0, 3)), 2 * d + 4 * int(rng.integers(0, 5))
+        off = 4 * int(rng.integers(0, (ld_y - d) // 4 + 1))
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        xb = torch.zeros(n, ld_x, device=dev)
+        xb[:, :d] = torch.from_numpy(x).to(dev)
+        c = hop.indices.cpu().numpy()
+        ref = O.spmm_coo(c[:, 0], c[:, 1], hop.values.cpu().numpy(), x, n)
+        for mode in ("csr", "tensor"):
+            yb = torch.full((n, ld_y), 7.0, device=dev)
+            HopPlan([hop], mode=mode).run(xb[:, :d], yb, [off], d=d)
+            got = yb.cpu().numpy()
+            assert util.rel_err(got[:, off:off + d], ref) <= TOL, (trial, mode, n, d, dens)
+            mask = np.ones(ld_y, dtype=bool)
+            mask[off:off + d] = False
+            assert (got[:, mask] == 7.0).all(), "columns outside the hop's slot must not be touched"
+
+
+def test_rw_normalised_hop_on_both_formats(dev):
+    """RW_NORMALIZED (_dataset.py:119-123): val = 1/deg_i.  Not a dinv_i*dinv_j factorisation -> CSR format only."""
+    from h2gcn_b200.datasets._dataset import TransformSPAdj
+    from h2gcn_b200.ops import HopPlan
+    O, _ = _oracle()
+    TransformSPAdj.device = dev
+    z = util.load_golden("planetoid_citeseer")
+    adj = O.remove_eye(util.raw_adj(z))
+    hop = TransformSPAdj.normalize(adj, TransformSPAdj.NType.RW_NORMALIZED)
+    ref_m = O.rw_normalize(adj)[0]
+    assert np.array_equal(hop.values.cpu().numpy(), ref_m.data.astype(np.float32))
+    n, d = adj.shape[0], 32
+    x = np.random.default_rng(0).standard_normal((n, d)).astype(np.float32)
+    y = torch.empty(n, d, device=dev)
+    plan = HopPlan([hop])
+    assert plan.tensor_idx == []
+    plan.run(torch.from_numpy(x).to(dev), y, [0])
+    assert util.rel_err(y.cpu().numpy(), (ref_m.astype(np.float32) @ x)) <= TOL
+
+
+def test_symmetric_hops_give_the_backward_pass(dev):
+    """the backward of Y = A X w.r.t. X is A^T dY; the hop adjacencies of the undirected graphs
+    the loaders build are symmetric (values dinv_i*dinv_j), so the SAME fused kernel computes the gradient.
+    Checked as the adjoint identity <A x, y> == <x, A y> on both formats."""
+    from h2gcn_b200.ops import HopPlan
+    z = util.load_golden("planetoid_cora")
+    hops = _norm_hops(dev, z)
+    n, d = hops[0].n_rows, 64
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, d, device=dev, generator=g)
+    y = torch.randn(n, d, device=dev, generator=g)
+    for mode in ("csr", "tensor"):
+        plan = HopPlan(hops, mode=mode)
+        ax, ay = torch.empty(n, 2 * d, device=dev), torch.empty(n, 2 * d, device=dev)
+        plan.run(x, ax, [0, d])
+        plan.run(y, ay, [0, d])
+        for h in range(2):
+            lhs = (ax[:, h * d:(h + 1) * d].double() * y.double()).sum().item()
+            rhs = (x.double() * ay[:, h * d:(h + 1) * d].double()).sum().item()
+            assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (mode, h, lhs, rhs)
