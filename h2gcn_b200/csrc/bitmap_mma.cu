@@ -668,8 +668,31 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
         BmSched &sc = h->sched[k];
         cta_ptr[k].assign(G + 1, 0);
         int n_slots = 0;
+        // Every (group, tile) item a CTA enters costs an epilogue (TMEM drain + write-out + pipeline refill, measured
+        // ~3 k cycles ~ 6 units of 512 cycles): ranges are cut at equal COST = units + kEpilogueUnits per item entered,
+        // so CTAs whose range crosses a tile boundary get fewer units.
+        constexpr int64_t kEpilogueUnits = 6;
+        std::vector<int64_t> item_start;
+        for (int64_t grp = 0; grp < ng; ++grp)
+            for (int64_t t = 0; t < nt; ++t)
+                if (tp[t + 1] > tp[t]) item_start.push_back(grp * n_units + tp[t]);
+        auto cost_at = [&](int64_t q) {   // cost of linear units [0, q)
+            return q + kEpilogueUnits * (int64_t)(std::lower_bound(item_start.begin(), item_start.end(), q) - item_start.begin());
+        };
+        const int64_t cost_total = cost_at(total);
+        auto bound_for = [&](int c) {
+            if (c <= 0) return (int64_t)0;
+            if (c >= G) return total;
+            const int64_t target = cost_total * c / G;
+            int64_t lo = 0, hi = total;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (cost_at(mid) < target) lo = mid + 1; else hi = mid;
+            }
+            return lo;
+        };
         for (int c = 0; c < G; ++c) {
-            const int64_t q0 = total * c / G, q1 = total * (c + 1) / G;
+            const int64_t q0 = bound_for(c), q1 = bound_for(c + 1);
             cta_ptr[k][c] = (int)segs[k].size();
             int64_t q = q0;
             while (q < q1) {
