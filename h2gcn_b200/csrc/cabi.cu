@@ -1,6 +1,7 @@
 // Library-level pieces of the C-ABI: error state, launch counter, and the host-buffer graph handle used by the
 // end-to-end entry points (include/h2gcn_b200.h, "end-to-end entry points with HOST buffers").
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -241,8 +242,10 @@ extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
     return H2_OK;
 }
 
-extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                              const int64_t *offsets, h2_stream_t s) {
+// y_host != nullptr: every hop's column block is copied back to the host buffer (same layout as Y) as soon as that hop
+// is done, so the write-back of the CSR hops overlaps the tensor-core hops.
+static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                            const int64_t *offsets, float *y_host, h2_stream_t s) {
     cudaStream_t st = (cudaStream_t)s;
     H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = graph_reserve(g, d);
@@ -270,12 +273,29 @@ extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t 
         }
         rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy, s);
         if (rc != H2_OK) return rc;
+        if (y_host)
+            for (int k = 0; k < g->n_csr; ++k) {
+                const int64_t off = offsets[g->csr_idx[k]];
+                H2_CUDA(cudaMemcpy2DAsync(y_host + off, (size_t)ldy * 4, Y + off, (size_t)ldy * 4, (size_t)d * 4,
+                                          (size_t)g->n_rows, cudaMemcpyDeviceToHost, st));
+            }
     }
     if (two) {
         H2_CUDA(cudaEventRecord(g->ev_join, g->side));
         H2_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
     }
+    if (y_host)
+        for (int k = 0; k < g->n_bm; ++k) {
+            const int64_t off = offsets[g->bm_idx[k]];
+            H2_CUDA(cudaMemcpy2DAsync(y_host + off, (size_t)ldy * 4, Y + off, (size_t)ldy * 4, (size_t)d * 4,
+                                      (size_t)g->n_rows, cudaMemcpyDeviceToHost, st));
+        }
     return H2_OK;
+}
+
+extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                              const int64_t *offsets, h2_stream_t s) {
+    return graph_round_impl(g, d, X, ldx, Y, ldy, offsets, nullptr, s);
 }
 
 extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s) {
@@ -287,9 +307,10 @@ extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host
     for (int h = 0; h < g->n_hops; ++h) offsets[h] = (int64_t)h * d;  // GCNLayer + Flatten layout: [N, H*d]
     const int64_t ldy = (int64_t)g->n_hops * d;
     H2_CUDA(cudaMemcpyAsync(g->x_dev, x_host, (size_t)g->n_cols * d * 4, cudaMemcpyHostToDevice, st));
-    int rc = h2_graph_round(g, d, g->x_dev, d, g->y_dev, ldy, offsets, s);
+    static const bool contiguous = getenv("H2_E2E_CONTIGUOUS_D2H") != nullptr;   // measurement switch
+    int rc = graph_round_impl(g, d, g->x_dev, d, g->y_dev, ldy, offsets, contiguous ? nullptr : y_host, s);
     if (rc != H2_OK) return rc;
-    H2_CUDA(cudaMemcpyAsync(y_host, g->y_dev, (size_t)g->n_rows * ldy * 4, cudaMemcpyDeviceToHost, st));
+    if (contiguous) H2_CUDA(cudaMemcpyAsync(y_host, g->y_dev, (size_t)g->n_rows * ldy * 4, cudaMemcpyDeviceToHost, st));
     H2_CUDA(cudaStreamSynchronize(st));
     return H2_OK;
 }
