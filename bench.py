@@ -270,6 +270,35 @@ def main():
     ms_per_step = total_ms / args.steps
     value = nnz_total * d / (ms_per_step * 1e-3)
 
+    # ---- precompute metric: exact-2-hop pattern + normalisation on the GPU, 2-paths/s and nnz2/s -----------
+    precompute = None
+    if world == 1:
+        from h2gcn_b200 import ops
+        a = adj.tocsr()
+        rp_d = torch.from_numpy(a.indptr.astype(np.int64)).to(dev)
+        col_d = torch.from_numpy(a.indices.astype(np.int32)).to(dev)
+        two_paths = int((np.diff(a.indptr).astype(np.int64) ** 2).sum())
+        for _ in range(2):
+            ops.hop2_pattern(rp_d, col_d)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            rp2_d, col2_d = ops.hop2_pattern(rp_d, col_d)        # count -> scan -> (host sync) -> fill
+            ops.sym_normalize(rp2_d, col2_d)
+        torch.cuda.synchronize()
+        t_gpu = (time.perf_counter() - t0) / reps
+        precompute = {"what": "nhoodSplit(adj, 2)[2] + SYM normalize on the GPU (h2_hop2_count/fill, h2_sym_normalize), "
+                              "host wall clock incl. the one count->alloc->fill sync",
+                      "seconds": t_gpu, "two_paths_per_s": two_paths / t_gpu, "nnz2_per_s": int(col2_d.numel()) / t_gpu,
+                      "two_paths": two_paths, "nnz2": int(col2_d.numel())}
+        if not args.no_cpu_baseline:
+            from oracle import cbind
+            t0 = time.perf_counter()
+            cbind.hop2_csr(a.indptr, a.indices)
+            precompute["cpu_port_seconds"] = time.perf_counter() - t0
+            precompute["cpu_port_cores"] = cbind.max_threads()
+
     # ---- e2e: the host-buffer C-ABI call (X host->device, round, Y device->host inside the timed region) -------------
     e2e = None
     if world == 1:
@@ -331,6 +360,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if precompute is not None:
+        line["config"]["precompute"] = precompute
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(g.hops_host(), x_full)
     print(json.dumps(line))

@@ -218,8 +218,10 @@ class GraphData:
         return SparseTensor.from_scipy(spmat, device)
 
     def getTensors(self, getDenseAdj=False, getAdjHops=None, getAdjNormHops=None,
-                   normType=TransformSPAdj.NType.SYM_NORMALIZED, dtype=np.float32):
-        """_dataset.py:537-584.  `adj_hops` is a list of device SparseTensors in the order of `getAdjNormHops`."""
+                   normType=TransformSPAdj.NType.SYM_NORMALIZED, dtype=np.float32, cache_dir=None):
+        """_dataset.py:537-584.  `adj_hops` is a list of device SparseTensors in the order of `getAdjNormHops`.
+        cache_dir: optional on-disk cache of the (merged, un-normalised) hop patterns keyed by a hash of the adjacency
+        (datasets/_cache.py); the normalisation is recomputed on load, so cached and fresh results are bit-identical."""
         dev = torch.device(self.device)
         TransformSPAdj.device = self.device
         tensors = Namespace()
@@ -235,9 +237,17 @@ class GraphData:
             hop_max = max(chain(*hops))
             if normType == TransformSPAdj.NType.CHEBY:
                 raise NotImplementedError("CHEBY hops are not used by any H2GCN config")
-            splits = TransformSPAdj.nhoodSplit(tensors.adj, hop_max)
             n = self.num_samples
-            merged = [splits[e[0]] if len(e) == 1 else _merge_patterns([splits[i] for i in e], n, n) for e in hops]
+            merged = key = None
+            if cache_dir is not None:
+                from . import _cache
+                key = _cache.graph_key(tensors.adj.rowptr.cpu().numpy(), tensors.adj.col.cpu().numpy(), getAdjNormHops, "pattern")
+                merged = _cache.load_hops(cache_dir, key, dev)
+            if merged is None:
+                splits = TransformSPAdj.nhoodSplit(tensors.adj, hop_max)
+                merged = [splits[e[0]] if len(e) == 1 else _merge_patterns([splits[i] for i in e], n, n) for e in hops]
+                if cache_dir is not None:
+                    _cache.save_hops(cache_dir, key, merged)
             tensors.adj_hops = [TransformSPAdj.normalize(x, normType) for x in merged]
         for key, value in self._dense_data.items():
             setattr(tensors, key, torch.as_tensor(np.asarray(value), dtype=torch.float32, device=dev))

@@ -82,3 +82,39 @@ def test_cli_forward_on_synthetic_planetoid(tmp_path):
     conf = parse_network_setup("M64-R-T1-G-V-T2-G-V-C1-C2-D0.5-MO", 4, _dense_units=64, _dropout_rate=0.5)
     ref = O.forward(conf, weights, (fi[:, 0], fi[:, 1], t["features"].values.cpu().numpy()), 300, hops)
     assert util.rel_err(logits.cpu().numpy(), ref) <= 1e-4
+
+
+def test_npz_adjacency_conventions(tmp_path):
+    """npz loader (reference npz-datasets/dataset.py:28-55): symmetrise, binarise, zero the diagonal."""
+    from h2gcn_b200.datasets.npz import NpzData, canonical_adjacency
+    a = sp.csr_matrix(np.array([[1, 1, 0, 0], [0, 0, 2, 0], [0, 1, 0, 0], [0, 0, 0, 0]], dtype=np.float64))
+    c = canonical_adjacency(a).toarray()
+    assert (c == np.array([[0, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 0]])).all()
+    feats = sp.csr_matrix(np.arange(12, dtype=np.float32).reshape(4, 3))
+    fn = str(tmp_path / "toy.npz")
+    np.savez(fn, adj_data=a.data, adj_indices=a.indices, adj_indptr=a.indptr, adj_shape=a.shape,
+             attr_data=feats.data, attr_indices=feats.indices, attr_indptr=feats.indptr, attr_shape=feats.shape,
+             labels=np.array([0, 1, 1, 2]), idx_train=np.array([0, 1]), idx_val=np.array([2]), idx_test=np.array([3]))
+    d = NpzData(fn, device="cpu")
+    assert d.num_labels == 3 and d.num_samples == 4 and d.feature_dim == 3
+    assert (sp.csr_matrix(d.sparse_adj).toarray() == c).all()
+    assert list(d.train_mask) == [True, True, False, False] and d.y_test[3, 2] == 1
+
+
+@pytest.mark.gpu
+def test_precompute_cache_round_trip(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from h2gcn_b200.datasets._dataset import GraphData
+    z = util.load_golden("planetoid_citeseer")
+    def tensors():
+        data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device="cuda")
+        data.adj_remove_eye()
+        return data.getTensors(getAdjNormHops=["1", "2"], cache_dir=str(tmp_path))
+    first = tensors()
+    assert len(os.listdir(tmp_path)) == 1
+    second = tensors()                       # served from the cache
+    for a, b, (gr, gc, gv) in zip(first.adj_hops, second.adj_hops, util.golden_hops(z)):
+        assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.col, b.col) and torch.equal(a.values, b.values)
+        assert np.array_equal(b.values.cpu().numpy(), gv) and np.array_equal(b.indices[:, 1].cpu().numpy(), gc)
