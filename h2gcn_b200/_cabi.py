@@ -18,7 +18,7 @@ c_i32, c_i64, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctyp
 class HopDesc(ctypes.Structure):
     """h2_hop_t"""
     _fields_ = [("rowptr", c_vp), ("col", c_vp), ("val", c_vp), ("dinv", c_vp), ("dinv_row", c_vp),
-                ("out_col_off", c_i64)]
+                ("out_col_off", c_i64), ("in_col_off", c_i64)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/h2gcn_b200.h declares (tests check this).
@@ -61,6 +61,8 @@ PROTOTYPES = {
     "h2_graph_formats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32)]),
     "h2_graph_round_host": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "h2_graph_round": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "h2_graph_round_multi": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "h2_sum_slices_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "h2_graph_destroy": (ctypes.c_int, [c_vp]),
 }
 

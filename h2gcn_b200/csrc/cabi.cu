@@ -196,7 +196,7 @@ extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, c
             if (e == cudaSuccess && nnz) e = cudaMemcpy(v, val_host[h], (size_t)nnz * 4, cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) return fail(cuda_fail(e, "h2_graph_create: upload"));
-        g->hops[h] = h2_hop_t{(const int64_t *)rp, (const int32_t *)c, (const float *)v, nullptr, nullptr, 0};
+        g->hops[h] = h2_hop_t{(const int64_t *)rp, (const int32_t *)c, (const float *)v, nullptr, nullptr, 0, 0};
     }
     if ((rc = graph_finish(g, want_bitmap))) return fail(rc);
     if ((rc = graph_reserve(g, d_max))) return fail(rc);
@@ -245,7 +245,7 @@ extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
 // y_host != nullptr: every hop's column block is copied back to the host buffer (same layout as Y) as soon as that hop
 // is done, so the write-back of the CSR hops overlaps the tensor-core hops.
 static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                            const int64_t *offsets, float *y_host, h2_stream_t s) {
+                            const int64_t *offsets, float *y_host, h2_stream_t s, const int64_t *x_offsets = nullptr) {
     cudaStream_t st = (cudaStream_t)s;
     H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = graph_reserve(g, d);
@@ -259,7 +259,8 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
     }
     for (int k = 0; k < g->n_bm; ++k) {
         const int h = g->bm_idx[k];
-        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X, ldx, g->dinv[h], g->xpack, g->xpack_bytes, (h2_stream_t)bm_stream);
+        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X + (x_offsets ? x_offsets[h] : 0), ldx, g->dinv[h], g->xpack,
+                              g->xpack_bytes, (h2_stream_t)bm_stream);
         if (rc != H2_OK) return rc;
         rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
                             offsets[h], g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
@@ -270,6 +271,7 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
         for (int k = 0; k < g->n_csr; ++k) {
             sub[k] = g->hops[g->csr_idx[k]];
             sub[k].out_col_off = offsets[g->csr_idx[k]];
+            sub[k].in_col_off = x_offsets ? x_offsets[g->csr_idx[k]] : 0;
         }
         rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy, s);
         if (rc != H2_OK) return rc;
@@ -296,6 +298,15 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
 extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                               const int64_t *offsets, h2_stream_t s) {
     return graph_round_impl(g, d, X, ldx, Y, ldy, offsets, nullptr, s);
+}
+
+extern "C" int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, const int64_t *x_offsets, float *Y,
+                                    int64_t ldy, const int64_t *y_offsets, h2_stream_t s) {
+    H2_REQUIRE(x_offsets, H2_ERR_INVALID, "h2_graph_round_multi: null x_offsets");
+    if (g) for (int h = 0; h < g->n_hops; ++h)
+        H2_REQUIRE(x_offsets[h] % 4 == 0 && x_offsets[h] >= 0 && x_offsets[h] + d <= ldx, H2_ERR_ALIGN,
+                   "h2_graph_round_multi: x_offsets[%d]=%lld", h, (long long)x_offsets[h]);
+    return graph_round_impl(g, d, X, ldx, Y, ldy, y_offsets, nullptr, s, x_offsets);
 }
 
 extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s) {

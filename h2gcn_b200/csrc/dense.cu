@@ -54,6 +54,19 @@ __global__ void relu_slice_kernel(int32_t n_rows, int32_t d, const float *__rest
     Y[r * ldy + c] = v;
 }
 
+__global__ void sum_slices_kernel(int32_t n_rows, int32_t d, int32_t n_slices, const float *__restrict__ T, int64_t ldt,
+                                  float *__restrict__ G, int64_t ldg, int accumulate, const float *__restrict__ mask_src,
+                                  int64_t ld_mask) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_rows * d) return;
+    const int64_t r = idx / d;
+    const int c = (int)(idx - r * d);
+    float a = accumulate ? G[r * ldg + c] : 0.f;
+    for (int s = 0; s < n_slices; ++s) a += T[r * ldt + (int64_t)s * d + c];   // fixed order
+    if (mask_src && !(mask_src[r * ld_mask + c] > 0.f)) a = 0.f;
+    G[r * ldg + c] = a;
+}
+
 }  // namespace h2
 
 using namespace h2;
@@ -80,5 +93,17 @@ extern "C" int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int6
     H2_REQUIRE(X && Y && ldx >= d && ldy >= d, H2_ERR_INVALID, "h2_relu_slice_f32: bad argument");
     relu_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>(n_rows, d, X, ldx, Y, ldy, relu);
     H2_LAUNCHED("relu_slice_kernel");
+    return H2_OK;
+}
+
+extern "C" int h2_sum_slices_f32(int32_t n_rows, int32_t d, int32_t n_slices, const float *T, int64_t ldt, float *G,
+                                 int64_t ldg, int32_t accumulate, const float *mask_src, int64_t ld_mask, h2_stream_t s) {
+    H2_REQUIRE(n_rows >= 0 && d >= 0 && n_slices >= 0, H2_ERR_INVALID, "h2_sum_slices_f32: bad sizes");
+    const int64_t total = (int64_t)n_rows * d;
+    if (total == 0) return H2_OK;
+    H2_REQUIRE(G && (T || n_slices == 0) && ldg >= d && ldt >= (int64_t)n_slices * d, H2_ERR_INVALID, "h2_sum_slices_f32: bad argument");
+    sum_slices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>(n_rows, d, n_slices, T, ldt, G, ldg, accumulate,
+                                                                                   mask_src, ld_mask);
+    H2_LAUNCHED("sum_slices_kernel");
     return H2_OK;
 }

@@ -27,6 +27,7 @@ struct HopDev {
     const float *dinv;
     const float *dinv_row;
     int64_t out_off;
+    int64_t in_off;
 };
 
 struct __align__(16) RowDesc {   // one schedule slot: where the virtual row's entries are, which row it is
@@ -204,7 +205,7 @@ fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     float4 acc[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_segment<LPR, NV>(hop.col, hop.val, hop.dinv, s, e, p.X, p.ldx, p.d4, lane, acc);
+    accumulate_segment<LPR, NV>(hop.col, hop.val, hop.dinv, s, e, p.X + hop.in_off, p.ldx, p.d4, lane, acc);
     reduce_groups<LPR, NV>(acc);
 
     const float scale = hop.val ? 1.f : __ldg(hop.dinv_row + i);  // factored mode: dinv_i * sum_j dinv_j x_j
@@ -365,7 +366,10 @@ int fill_round_params(RoundParams &p, const PlanHost *ph, const void *plan_dev, 
         H2_REQUIRE(hops[h].out_col_off % 4 == 0 && hops[h].out_col_off >= 0 && hops[h].out_col_off + d <= ldy,
                    H2_ERR_ALIGN, "fused round: hop %d out_col_off=%lld (d=%d, ldy=%lld)", h,
                    (long long)hops[h].out_col_off, d, (long long)ldy);
-        p.hop[h] = HopDev{hops[h].rowptr, hops[h].col, hops[h].val, hops[h].dinv, hops[h].dinv_row, hops[h].out_col_off};
+        H2_REQUIRE(hops[h].in_col_off % 4 == 0 && hops[h].in_col_off >= 0 && hops[h].in_col_off + d <= ldx, H2_ERR_ALIGN,
+                   "fused round: hop %d in_col_off=%lld (d=%d, ldx=%lld)", h, (long long)hops[h].in_col_off, d, (long long)ldx);
+        p.hop[h] = HopDev{hops[h].rowptr, hops[h].col, hops[h].val, hops[h].dinv, hops[h].dinv_row, hops[h].out_col_off,
+                          hops[h].in_col_off};
     }
     p.perm = (const RowDesc *)plan_dev;
     p.X = X; p.Y = Y; p.bias = nullptr;
@@ -429,7 +433,7 @@ extern "C" int h2_sparse_dense_f32(int32_t n_rows, const int64_t *rowptr, const 
         return H2_OK;
     }
     RoundParams rp;
-    rp.hop[0] = HopDev{rowptr, col, val, nullptr, nullptr, out_col_off};
+    rp.hop[0] = HopDev{rowptr, col, val, nullptr, nullptr, out_col_off, 0};
     rp.perm = nullptr;
     rp.X = W; rp.Y = Y; rp.bias = bias;
     rp.ldx = p; rp.ldy = ldy;

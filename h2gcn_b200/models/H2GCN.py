@@ -63,8 +63,20 @@ def initialize_model(args, layer_setups, optimizer, lr, l2_regularize_weight, ea
     checkpoints, early stopping) is outside the accelerated path (SURVEY.md §2 #2, #7)."""
     model = H2GCN(layer_setups, l2_regularize_weight=l2_regularize_weight)
 
+    state = dict(opt=None)
+
     def train_step(adj, adj_hops, features, y_train, train_mask, **kwargs):
-        raise NotImplementedError("training (backward of the hop SpMM) is a 'next' row — SURVEY.md §8f rank 1")
+        """H2GCN.py:66-74: forward (training=True), masked softmax-CE + l2, backward, optimizer step."""
+        loss, grads = model.loss_and_grads(adj, features, adj_hops, y_train, train_mask)
+        params = model.trainable_variables
+        if state["opt"] is None:
+            if str(optimizer).lower() != "adam":
+                raise NotImplementedError("only --optimizer adam is wired up")
+            state["opt"] = torch.optim.Adam(params, lr=lr, eps=1e-7)     # keras Adam defaults
+        for w, g in zip(params, grads):
+            w.grad = g
+        state["opt"].step()
+        return dict(train_loss=loss)
 
     def predict_step(adj, adj_hops, features, **kwargs):
         return model(adj, features, adj_hops, training=False)
@@ -167,7 +179,48 @@ class _FusedProgram:
         self.adjhops = adjhops
         self.ok = True
 
-    def run(self, features):
+    # ---- training: same launch sequence forward, mirrored offsets backward ------------------
+    def train_forward(self, features, dropout_rate, generator=None):
+        """Forward with dropout on the classifier input (keras Dropout, H2GCN.py:257); keeps what backward needs."""
+        logits_in = self.run(features, classify=False)
+        keep = 1.0 - dropout_rate
+        if dropout_rate > 0:
+            self._mask = (torch.rand(logits_in.shape, device=logits_in.device, generator=generator) < keep).float() / keep
+            self._dropped = logits_in * self._mask
+        else:
+            self._mask, self._dropped = None, logits_in
+        self._features = features
+        return self.out_layer(self._dropped)
+
+    def backward(self, dlogits, features_t):
+        """Gradients of the kernels of the first dense layer and of the classifier for d(loss)/d(logits) = dlogits.
+        The aggregation rounds run backwards through the SAME fused kernels: A_h is symmetric, so dX = sum_h A_h dY_h
+        with hop h reading its own slice of the gradient buffer (`HopPlan.run_multi`) and `sum_slices` adding them."""
+        W_out = self.out_layer.kernel
+        gW_out = self._dropped.t() @ dlogits                      # [W, C] dense contraction (library GEMM)
+        gfinal = dlogits @ W_out.t()
+        if self._mask is not None:
+            gfinal = gfinal * self._mask
+        gbuf = torch.zeros_like(self.buf)
+        gbuf[:, :self.final_width] = gfinal
+        gW0 = None
+        for lid in reversed(self.steps):
+            lf, o = self.leaves[lid], self.off[lid]
+            if lf["kind"] == "gcn":
+                plan = lf["layer"].plan_for(self.adjhops)
+                so, d, nh = self.off[lf["src"][0]], lf["d"], lf["nh"]
+                tmp = torch.empty(self.buf.shape[0], nh * d, dtype=torch.float32, device=self.buf.device)
+                plan.run_multi(gbuf, [o + h * d for h in range(nh)], tmp, [h * d for h in range(nh)], d)
+                ops.sum_slices(tmp, d, nh, gbuf[:, so:so + d], accumulate=True)
+            else:
+                p = lf["width"]
+                g0 = gbuf[:, o:o + p]
+                if lf["relu"]:
+                    ops.sum_slices(g0, p, 0, g0, accumulate=True, mask_src=self.buf[:, o:o + p])   # g0 *= (r0 > 0)
+                gW0 = ops.sparse_dense(features_t, g0.contiguous())        # X^T . dr0  ->  [F, p]
+        return gW0, gW_out
+
+    def run(self, features, classify=True):
         buf = self.buf
         for lid in self.steps:
             lf, o = self.leaves[lid], self.off[lid]
@@ -177,6 +230,8 @@ class _FusedProgram:
                 plan = lf["layer"].plan_for(self.adjhops)
                 so, d = self.off[lf["src"][0]], lf["d"]
                 plan.run(buf[:, so:so + d], buf, [o + h * d for h in range(lf["nh"])], d=d)
+        if not classify:
+            return buf[:, :self.final_width]
         return self.out_layer(buf[:, :self.final_width])
 
 
@@ -326,6 +381,35 @@ class H2GCN:
         if addSupervision:
             return inputs, supervisedOutputs
         return inputs
+
+    def loss_and_grads(self, adj, inputs, adjhops, labels, mask, dropout_rate=None, generator=None):
+        """Training forward + backward on the fused program.  Loss = masked softmax cross-entropy
+        (h2gcn/models/_metrics.py:8-16) + sum_k l2 * ||W_k||^2 (keras.regularizers.l2, H2GCN.py:239-248, :363-367).
+        Returns (loss, [dL/dW0, dL/dW_out]) in the order of `trainable_variables`."""
+        prog = self._fused_program(inputs, adjhops)
+        if not prog.ok:
+            raise NotImplementedError("training is implemented for the fused layer-list family only")
+        if any(getattr(l, "use_bias", False) for l in self.layer_objs):
+            raise NotImplementedError("training with bias terms (F layers) is not wired up")
+        if dropout_rate is None:
+            rates = [l.rate for l in self.layer_objs if isinstance(l, layers.Dropout)]
+            dropout_rate = rates[-1] if rates else 0.0
+        key = id(inputs)
+        if getattr(self, "_feat_t_key", None) != key:      # X^T as CSR, once per feature tensor (for dW0 = X^T dr0)
+            xt = inputs.to_scipy().T.tocsr()
+            self._feat_t = ops.SparseTensor.from_scipy(xt, inputs.device)
+            self._feat_t_key = key
+        logits = prog.train_forward(inputs, dropout_rate, generator)
+        m = mask / mask.sum()
+        logp = torch.log_softmax(logits, dim=1)
+        ce = -(labels * logp).sum(1)
+        l2 = self.l2_regularize_weight
+        params = self.trainable_variables
+        loss = (ce * m).sum() + sum(l2 * (w * w).sum() for w in params)
+        dlogits = (torch.softmax(logits, dim=1) * labels.sum(1, keepdim=True) - labels) * m[:, None]
+        gW0, gW_out = prog.backward(dlogits.contiguous(), self._feat_t)
+        grads = [gW0 + 2 * l2 * params[0], gW_out + 2 * l2 * params[1]]
+        return float(loss), grads
 
     def callOutputNetwork(self, adj, inputs, adjhops, training=False, returnBefore=0, **kwargs):
         return self(adj, inputs, adjhops, training, returnBefore, self.output_ind, **kwargs)

@@ -238,6 +238,21 @@ class HopPlan:
         check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(out), out.stride(0), offs, stream_ptr(stream)))
         return out
 
+    def run_multi(self, x, x_offsets, out, offsets, d, stream=None):
+        """Backward-style round: out[:, offsets[h] : +d] = hops[h] @ x[:, x_offsets[h] : +d] — every hop reads ITS OWN
+        column slice of `x`.  With the symmetric hop adjacencies of undirected graphs this is the transposed product
+        of the backward pass (dX = sum_h A_h^T dY_h; sum the slices with `sum_slices`)."""
+        require_cuda(x, out)
+        if x.dtype != torch.float32 or out.dtype != torch.float32 or x.stride(-1) != 1 or out.stride(-1) != 1:
+            raise ValueError("fused round computes in fp32 on row-major buffers")
+        if x.shape[0] != self.n_cols or out.shape[0] != self.n_rows or len(offsets) != len(self.hops) or \
+                len(x_offsets) != len(self.hops):
+            raise ValueError("shape mismatch / one offset per hop")
+        xo = (ctypes.c_int64 * len(x_offsets))(*x_offsets)
+        yo = (ctypes.c_int64 * len(offsets))(*offsets)
+        check(lib().h2_graph_round_multi(self._h, d, ptr(x), x.stride(0), xo, ptr(out), out.stride(0), yo, stream_ptr(stream)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib().h2_graph_destroy(self._h)
@@ -248,6 +263,14 @@ class HopPlan:
             self.close()
         except Exception:
             pass
+
+
+def sum_slices(t, d, n_slices, g, accumulate=False, mask_src=None, stream=None):
+    """g[:, :d] (+)= sum_s t[:, s*d:(s+1)*d], optionally zeroed where mask_src <= 0 (ReLU gradient)."""
+    require_cuda(t, g, mask_src)
+    check(lib().h2_sum_slices_f32(g.shape[0], d, n_slices, ptr(t), t.stride(0), ptr(g), g.stride(0), int(accumulate),
+                                  ptr(mask_src), 0 if mask_src is None else mask_src.stride(0), stream_ptr(stream)))
+    return g
 
 
 def sparse_dense(feat, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None):

@@ -55,6 +55,8 @@ typedef struct {
     const float *dinv;     /* [n_cols] column scale, only read when val == NULL */
     const float *dinv_row; /* [n_rows] row scale of the LOCAL rows (= dinv + row_begin), only read when val == NULL */
     int64_t out_col_off;   /* column offset (elements) inside the output row */
+    int64_t in_col_off;    /* column offset (elements) inside the input row: 0 in the forward pass; in the backward pass hop h
+                              reads ITS slice of the gradient (dX = sum_h A_h^T dY_h, A_h symmetric) */
 } h2_hop_t;
 
 /* ---- library / errors -------------------------------------------------------------------------------------- */
@@ -186,6 +188,12 @@ int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_
 /* same round on DEVICE buffers (X [n_cols, d] ld=ldx; Y: hop h at column offsets[h]); enqueues, does not synchronise. */
 int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                    const int64_t *offsets_host, h2_stream_t s);
+/* backward-style round: hop h reads X[:, x_offsets[h] : +d] (its own slice) and writes Y[:, y_offsets[h] : +d]. */
+int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, const int64_t *x_offsets_host, float *Y,
+                         int64_t ldy, const int64_t *y_offsets_host, h2_stream_t s);
+/* G[:, 0:d] (+)= sum_s T[:, s*d : (s+1)*d], optionally masked by (mask_src > 0) (ReLU gradient).  accumulate != 0: add to G. */
+int h2_sum_slices_f32(int32_t n_rows, int32_t d, int32_t n_slices, const float *T, int64_t ldt, float *G, int64_t ldg,
+                      int32_t accumulate, const float *mask_src, int64_t ld_mask, h2_stream_t s);
 int h2_graph_destroy(h2_graph_t *g);
 
 #ifdef __cplusplus

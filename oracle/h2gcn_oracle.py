@@ -230,3 +230,46 @@ def forward(layer_setups, weights, feat_coo, n_rows, adjhops, sparse_input=True,
         if tag:
             tagged[tag] = x
     return (x, acts) if return_activations else x
+
+
+# ----------------------------------------------------------------------------------------------------------
+# training step of the H2GCN-K family (test infrastructure for SURVEY.md §8f rank 1)
+# ----------------------------------------------------------------------------------------------------------
+def loss_and_grads(n_rounds, relu, W0, W_out, feat_csr, hops_csr, labels, mask, l2=0.0, drop_mask=None):
+    """fp64 restatement of one training forward/backward for 'M<p>[-R]-T1-(G-V-T<k>)*K-C..-D-MO' models.
+
+    Forward: r0 = act(X W0); r_k = [A1 r_{k-1} | A2 r_{k-1}]; final = [r_K | r0 | r1 | ... | r_{K-1}] (the concat order
+    of _layers.py:90-96 as laid out by H2GCN.py:273-278); logits = (final * drop_mask) W_out.
+    Loss (H2GCN.py:363-367, _metrics.py:8-16): sum_i m_i CE(logits_i, y_i) with m = mask / sum(mask), plus
+    l2 * (||W0||^2 + ||W_out||^2) (keras.regularizers.l2).  TensorFlow differentiates this with autograd; the
+    gradients below are the analytic ones.  hops_csr: scipy CSR matrices; returns (loss, dW0, dW_out)."""
+    X = sp.csr_matrix(feat_csr).astype(np.float64)
+    A = [sp.csr_matrix(a).astype(np.float64) for a in hops_csr]
+    W0 = np.asarray(W0, dtype=np.float64)
+    W_out = np.asarray(W_out, dtype=np.float64)
+    z0 = X @ W0
+    r = [np.maximum(z0, 0) if relu else z0]
+    for _ in range(n_rounds):
+        r.append(np.concatenate([a @ r[-1] for a in A], axis=1))
+    order = [n_rounds] + list(range(n_rounds)) if n_rounds else [0]
+    final = np.concatenate([r[k] for k in order], axis=1)
+    dm = np.ones_like(final) if drop_mask is None else np.asarray(drop_mask, dtype=np.float64)
+    logits = (final * dm) @ W_out
+    y = np.asarray(labels, dtype=np.float64)
+    m = np.asarray(mask, dtype=np.float64)
+    m = m / m.sum()
+    zmax = logits.max(1, keepdims=True)
+    logp = logits - zmax - np.log(np.exp(logits - zmax).sum(1, keepdims=True))
+    loss = float((-(y * logp).sum(1) * m).sum() + l2 * ((W0 ** 2).sum() + (W_out ** 2).sum()))
+    dlogits = (np.exp(logp) * y.sum(1, keepdims=True) - y) * m[:, None]
+    dW_out = (final * dm).T @ dlogits + 2 * l2 * W_out
+    dfinal = (dlogits @ W_out.T) * dm
+    widths = [r[k].shape[1] for k in order]
+    offs = np.concatenate([[0], np.cumsum(widths)])
+    g = {k: dfinal[:, offs[i]:offs[i + 1]].copy() for i, k in enumerate(order)}
+    for k in range(n_rounds, 0, -1):
+        d = r[k - 1].shape[1]
+        g[k - 1] = g[k - 1] + sum(a.T @ g[k][:, h * d:(h + 1) * d] for h, a in enumerate(A))
+    g0 = g[0] * (z0 > 0) if relu else g[0]
+    dW0 = X.T @ g0 + 2 * l2 * W0
+    return loss, np.asarray(dW0), np.asarray(dW_out)

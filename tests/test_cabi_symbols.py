@@ -45,7 +45,7 @@ def test_ctypes_table_matches_header(built):
 
 def test_hop_struct_layout():
     from h2gcn_b200 import _cabi
-    assert ctypes.sizeof(_cabi.HopDesc) == 48  # 5 pointers + int64, matches h2_hop_t
+    assert ctypes.sizeof(_cabi.HopDesc) == 56  # 5 pointers + 2 x int64, matches h2_hop_t
 
 
 def test_argument_errors_surface_as_python_exceptions(built):

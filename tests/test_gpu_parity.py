@@ -479,3 +479,38 @@ def test_symmetric_hops_give_the_backward_pass(dev):
             lhs = (ax[:, h * d:(h + 1) * d].double() * y.double()).sum().item()
             rhs = (x.double() * ay[:, h * d:(h + 1) * d].double()).sum().item()
             assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs)), (mode, h, lhs, rhs)
+
+
+# ---- next row f1: training step (backward of the hop SpMM through the same kernels) -----------------------------------
+@pytest.mark.parametrize("name,setup,rounds,relu", [("planetoid_cora", "h2gcn2", 2, True), ("planetoid_cora", "h2gcn2_norelu", 2, False),
+                                                    ("planetoid_cora", "h2gcn1", 1, True), ("tiny_rand40", "h2gcn2", 2, True),
+                                                    ("planetoid_citeseer", "h2gcn2", 2, True)])
+def test_training_gradients_vs_oracle(dev, name, setup, rounds, relu):
+    from h2gcn_b200.datasets._dataset import GraphData
+    from h2gcn_b200.models import parse_network_setup
+    from h2gcn_b200.models.H2GCN import H2GCN
+    O, _ = _oracle()
+    z = util.load_golden(name)
+    n, F, C = int(z["feat_shape"][0]), int(z["feat_shape"][1]), int(z["num_labels"])
+    data = GraphData(util.raw_adj(z), util.raw_feat(z).tolil(), device=dev)
+    with np.errstate(divide="ignore"):
+        data.row_normalize_features()
+    data.adj_remove_eye()
+    t = data.getTensors(getAdjNormHops=["1", "2"])
+    l2 = 5e-4
+    model = H2GCN(parse_network_setup(str(z[f"{setup}/setup"]), C, _dense_units=64, _dropout_rate=0.5), l2_regularize_weight=l2)
+    W = util.weights_of(z, setup)
+    model.set_weights(W, device=dev)
+    rng = np.random.default_rng(3)
+    y = np.eye(C)[rng.integers(0, C, size=n)].astype(np.float32)
+    m = (rng.random(n) < 0.3).astype(np.float32)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    loss, grads = model.loss_and_grads(t.adj, t.features, t.adj_hops, torch.from_numpy(y).to(dev), torch.from_numpy(m).to(dev),
+                                       generator=gen)
+    prog = model._fused_program(t.features, t.adj_hops)
+    dm = None if prog._mask is None else prog._mask.cpu().numpy()
+    hops = [sp.csr_matrix((v, (r, c)), shape=(n, n)) for r, c, v in util.golden_hops(z)]
+    X = sp.csr_matrix((z["featn_vals"], (z["featn_rows"], z["featn_cols"])), shape=(n, F))
+    ref_loss, g0, g1 = O.loss_and_grads(rounds, relu, W[0], W[1], X, hops, y, m, l2=l2, drop_mask=dm)
+    assert abs(loss - ref_loss) <= 1e-4 * max(1.0, abs(ref_loss))
+    assert util.rel_err(grads[0].cpu().numpy(), g0) <= 2e-4 and util.rel_err(grads[1].cpu().numpy(), g1) <= 2e-4

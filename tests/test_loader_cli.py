@@ -71,10 +71,15 @@ def test_cli_forward_on_synthetic_planetoid(tmp_path):
     assert logits.shape == (300, 4)
     for key in ("tensors", "model", "train_step", "test_step", "predict_step", "embed_step", "dataset"):
         assert key in args.objects
-    with pytest.raises(NotImplementedError):
-        args.objects["train_step"](**args.objects["tensors"])
+    # train_step (H2GCN.py:66-74) runs on the same kernels: the loss goes down on the synthetic labels
+    tensors = args.objects["tensors"]
+    tensors["train_mask"] = torch.ones_like(tensors["train_mask"])
+    tensors["y_train"] = tensors["y_all"]
+    losses = [args.objects["train_step"](**tensors)["train_loss"] for _ in range(60)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.02, losses[::10]
     # same forward through the oracle with the model's weights
     model, t = args.objects["model"], args.objects["tensors"]
+    logits = args.objects["predict_step"](**t)              # with the trained weights
     weights = [w.cpu().numpy() for w in model.trainable_variables]
     fi = t["features"].indices.cpu().numpy()
     hops = [(h.indices[:, 0].cpu().numpy(), h.indices[:, 1].cpu().numpy(), h.values.cpu().numpy()) for h in t["adj_hops"]]
