@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "csr", "tensor"],
                     help="hop storage: auto = by density (dense-ish hops on tcgen05), csr = fp32 gather everywhere")
     ap.add_argument("--streams", type=int, default=2, help="caller streams the independent steps are issued on (round-robin)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="N>1: hop-boundary exchange (p2p = fused into the pack kernel over peer memory)")
     ap.add_argument("--splits", type=int, default=2, help="bf16 pieces of X on the tensor-core path (2 or 3)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -187,7 +188,7 @@ def main():
     adj = build_workload(n, E_PER_GPU * world, seed=0)
     d = FEAT
     t0 = time.perf_counter()
-    g = ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=args.splits)
+    g = ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=args.splits, exchange=args.exchange)
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0
     # R independent replicas of the round's whole working set (graph arrays, X, Y, scratch), visited round-robin, so
@@ -195,10 +196,16 @@ def main():
     # bitmap of the dense hop + CSR of the sparse hop + X, packed X, partial tiles (~3 x N d 4) + Y
     ws_est = g.n_local * n // 8 + 8 * (g.nnz1_global // world) + 3 * n * d * 4 + 2 * g.n_local * d * 4
     R = max(3, min(8, -(-(2 * L2_BYTES) // max(1, ws_est))))
-    graphs = [g] + [ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=args.splits)
+    R = -(-R // args.streams) * args.streams   # a multiple of the stream count: a replica always runs on the same stream
+    graphs = [g] + [ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=args.splits, exchange=args.exchange)
                     for _ in range(R - 1)]
     x_full = synth.features(n, d, 0)
     xs = [torch.from_numpy(x_full[g.row_begin:g.row_end]).to(dev) for _ in range(R)]
+    if world > 1 and g.exchange == "p2p":        # inputs live in symmetric memory: the exchange is zero-copy
+        for r in range(R):
+            buf = graphs[r].input_buffer(d)
+            buf.copy_(xs[r])
+            xs[r] = buf
     ys = [torch.empty(g.n_local, 2 * d, device=dev) for _ in range(R)]
     x_local, y = xs[0], ys[0]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -342,6 +349,8 @@ def main():
         "config": {"workload": f"uniform random graph |V|={n} |E|={E_PER_GPU * world} d={d} fp32 "
                                f"({'factored dinv' if args.factored else 'explicit fp32'} adjacency values), seed 0, "
                                f"rows sharded over {world} GPU(s)",
+                   "exchange": (g.exchange + (" (all-gather fused into the pack kernel: peer-memory loads over NVLink)"
+                                              if g.exchange == "p2p" else " all-gather, then the round")) if world > 1 else None,
                    "n_vertices": n, "nnz1": g.nnz1_global, "nnz2_local": g.nnz2_local, "nnz_local": g.nnz_local,
                    "nnz_total": nnz_total, "max_row_nnz": g.max_row_nnz, "kernel": g.plan.kernel_name,
                    "l2": f"inputs larger than L2: {R} independent replicas of the working set (graph arrays, X, Y, scratch; "

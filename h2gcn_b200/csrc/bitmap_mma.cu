@@ -124,10 +124,29 @@ __global__ void bm_tile_ptr_kernel(int32_t n_tiles, int32_t n_chunks, const int6
 // X' packing: fp32 X (row-major, ld) -> per 64-row chunk a [S*DG x 64] bf16 K-major tile, 128-byte swizzled, i.e.
 // byte-for-byte the shared-memory image the UMMA B descriptor expects.  n = s*DG + f, k = j % 64.
 // ------------------------------------------------------------------------------------------------------------------
+// Row source of the round input: rows [bound[q], bound[q+1]) live at ptr[q] (row-major, leading dimension ld).  With one
+// part this is a plain matrix; with several parts the pointers are the ranks' row shards mapped over NVLink (peer /
+// symmetric memory), i.e. the hop-boundary all-gather is fused into this kernel's loads.
+struct PackSrc {
+    const float *ptr[8];
+    int32_t bound[9];
+    int32_t n_parts;
+    int32_t pad;
+    int64_t ld;
+};
+
+__device__ __forceinline__ const float *pack_src_row(const PackSrc &src, int j) {
+    int q = 0;
+#pragma unroll
+    for (int t = 1; t < 8; ++t) q += (t < src.n_parts && j >= src.bound[t]) ? 1 : 0;
+    return src.ptr[q] + (int64_t)(j - src.bound[q]) * src.ld;
+}
+
 template <int DG>
 __global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d, int32_t n_groups, int32_t splits,
-                                                      const float *__restrict__ X, int64_t ldx,
-                                                      const float *__restrict__ dinv, uint4 *__restrict__ out) {
+                                                      const __grid_constant__ PackSrc src,
+                                                      const float *__restrict__ dinv, uint4 *__restrict__ out,
+                                                      float *__restrict__ xfull, int64_t ld_full) {
     __shared__ float s_x[kChunkCols][DG + 1];
     const int chunk = blockIdx.x, g = blockIdx.y;
     const int j0 = chunk * kChunkCols, f0 = g * DG;
@@ -138,7 +157,8 @@ __global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d,
         const int j = j0 + k;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < n_cols && f0 + f4 < d) {   // d % 4 == 0: a float4 is either fully inside or fully outside
-            v = __ldg(reinterpret_cast<const float4 *>(X + (int64_t)j * ldx + f0 + f4));
+            v = *reinterpret_cast<const float4 *>(pack_src_row(src, j) + f0 + f4);   // plain load: may be peer memory
+            if (xfull) *reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full + f0 + f4) = v;   // gathered fp32 copy
             const float sc = dinv ? __ldg(dinv + j) : 1.f;
             v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
         }
@@ -173,6 +193,15 @@ __global__ void __launch_bounds__(256) bm_pack_kernel(int32_t n_cols, int32_t d,
             }
         }
     }
+}
+
+// fp32 gather of the row shards into one matrix (rounds whose hops are all CSR)
+__global__ void gather_rows_kernel(int32_t n_cols, int32_t d4, const __grid_constant__ PackSrc src, float *__restrict__ xfull,
+                                   int64_t ld_full) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_cols * d4) return;
+    const int j = (int)(idx / d4), c = (int)(idx % d4);
+    reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full)[c] = reinterpret_cast<const float4 *>(pack_src_row(src, j))[c];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -496,7 +525,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     const int rr = lane / kLanesPerRow, c = (lane % kLanesPerRow) * 4;
                     const int row0 = half * 128 + quarter * 32;
                     const bool col_ok = c + 4 <= valid_cols && (kProducerSets == 1 || (c / 32) % kProducerSets == set);
-#pragma unroll 4
+#pragma unroll
                     for (int j = 0; j < 32; j += kRowsPerInstr) {
                         const int row = j + rr;
                         const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + c);
@@ -741,20 +770,64 @@ extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t sp
     return (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4 + 256;
 }
 
-// X' = diag(dinv_col) X packed into bf16 pieces — shared by every bitmap hop of a round that uses the same dinv_col.
-extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx,
-                                const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
-    H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && (splits == 2 || splits == 3) && X && xpack && ldx >= d, H2_ERR_INVALID,
-               "h2_bm_pack_x_f32: bad argument (d=%d splits=%d)", d, splits);
+namespace h2 {
+static int fill_src(PackSrc &src, int32_t n_cols, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld) {
+    H2_REQUIRE(n_parts >= 1 && n_parts <= 8 && ptrs && bounds && bounds[0] == 0 && bounds[n_parts] == n_cols, H2_ERR_INVALID,
+               "row shards: n_parts=%d (1..8), bounds must run from 0 to n_cols=%d", n_parts, n_cols);
+    memset(&src, 0, sizeof(src));
+    src.n_parts = n_parts; src.ld = ld;
+    for (int q = 0; q < n_parts; ++q) {
+        H2_REQUIRE((ptrs[q] || bounds[q + 1] == bounds[q]) && bounds[q + 1] >= bounds[q] && aligned16(ptrs[q]), H2_ERR_INVALID,
+                   "row shards: part %d null / unordered / misaligned", q);
+        src.ptr[q] = ptrs[q];
+        src.bound[q] = (int32_t)bounds[q];
+    }
+    for (int q = n_parts; q <= 8; ++q) src.bound[q] = n_cols;
+    return H2_OK;
+}
+
+// pack from row shards (n_parts pointers + bounds); xfull != nullptr also writes the gathered fp32 matrix
+int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
+                  int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
+                  h2_stream_t s) {
+    H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && (splits == 2 || splits == 3) && xpack && ld >= d && ld % 4 == 0,
+               H2_ERR_INVALID, "bm_pack: bad argument (d=%d splits=%d)", d, splits);
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
-               "h2_bm_pack_x_f32: xpack buffer too small / misaligned");
+               "bm_pack: xpack buffer too small / misaligned");
+    H2_REQUIRE(!xfull || (ld_full >= d && ld_full % 4 == 0 && aligned16(xfull)), H2_ERR_ALIGN, "bm_pack: xfull alignment");
+    PackSrc src;
+    int rc = fill_src(src, n_cols, n_parts, ptrs, bounds, ld);
+    if (rc != H2_OK) return rc;
     const int dg = dg_for(d, splits);
     dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for(d, dg));
     cudaStream_t st = (cudaStream_t)s;
-    if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
-    else bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, X, ldx, dinv_col, (uint4 *)xpack);
+    if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, src, dinv_col, (uint4 *)xpack, xfull, ld_full);
+    else bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, src, dinv_col, (uint4 *)xpack, xfull, ld_full);
     H2_LAUNCHED("bm_pack_kernel");
     return H2_OK;
+}
+
+int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
+                float *xfull, int64_t ld_full, h2_stream_t s) {
+    H2_REQUIRE(n_cols >= 0 && d > 0 && d % 4 == 0 && xfull && ld % 4 == 0 && ld_full % 4 == 0 && ld >= d && ld_full >= d &&
+               aligned16(xfull), H2_ERR_INVALID, "gather_rows: bad argument");
+    if (n_cols == 0) return H2_OK;
+    PackSrc src;
+    int rc = fill_src(src, n_cols, n_parts, ptrs, bounds, ld);
+    if (rc != H2_OK) return rc;
+    const int64_t total = (int64_t)n_cols * (d / 4);
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>(n_cols, d / 4, src, xfull, ld_full);
+    H2_LAUNCHED("gather_rows_kernel");
+    return H2_OK;
+}
+}  // namespace h2
+
+// X' = diag(dinv_col) X packed into bf16 pieces — shared by every bitmap hop of a round that uses the same dinv_col.
+extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx,
+                                const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
+    H2_REQUIRE(X && aligned16(X), H2_ERR_INVALID, "h2_bm_pack_x_f32: null / misaligned X");
+    const int64_t bounds[2] = {0, n_cols};
+    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s);
 }
 
 template <int DG, int S>

@@ -244,13 +244,53 @@ extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
 
 // y_host != nullptr: every hop's column block is copied back to the host buffer (same layout as Y) as soon as that hop
 // is done, so the write-back of the CSR hops overlaps the tensor-core hops.
+namespace h2 {
+int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
+                  int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
+                  h2_stream_t s);
+int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
+                float *xfull, int64_t ld_full, h2_stream_t s);
+}
+
+struct RoundParts {   // the round input as row shards (device / peer pointers) + the scratch for its gathered fp32 copy
+    int32_t n_parts;
+    const float *const *ptrs;
+    const int64_t *bounds;
+    int64_t ld;
+    float *xfull;
+    int64_t ld_full;
+};
+
 static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
-                            const int64_t *offsets, float *y_host, h2_stream_t s, const int64_t *x_offsets = nullptr) {
+                            const int64_t *offsets, float *y_host, h2_stream_t s, const int64_t *x_offsets = nullptr,
+                            const RoundParts *parts = nullptr) {
     cudaStream_t st = (cudaStream_t)s;
-    H2_REQUIRE(g && X && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
+    H2_REQUIRE(g && (X || parts) && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = graph_reserve(g, d);
     if (rc != H2_OK) return rc;
     const bool two = g->n_csr && g->n_bm;
+    int first_bm = 0;
+    if (parts) {
+        // Row-sharded input: the all-gather is fused into the first consumer.  With tensor-core hops the pack kernel
+        // reads the peers' shards directly and also leaves the gathered fp32 copy the CSR hops need; it runs BEFORE
+        // the fork so that both streams see its output.  Without tensor-core hops a plain gather kernel does it.
+        H2_REQUIRE(!x_offsets, H2_ERR_INVALID, "h2_graph_round: row shards and per-hop input offsets cannot be combined");
+        H2_REQUIRE(!g->n_csr || parts->xfull, H2_ERR_INVALID, "h2_graph_round_parts: CSR hops need the x_full scratch");
+        if (g->n_bm) {
+            const int h = g->bm_idx[0];
+            rc = bm_pack_parts(g->n_cols, d, g->splits, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, g->dinv[h],
+                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s);
+            if (rc != H2_OK) return rc;
+            first_bm = 1;
+        } else {
+            rc = gather_rows(g->n_cols, d, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, parts->xfull,
+                             parts->ld_full, s);
+            if (rc != H2_OK) return rc;
+        }
+        H2_REQUIRE(!(g->n_bm > 1) || parts->xfull, H2_ERR_INVALID, "h2_graph_round_parts: several tensor hops need x_full");
+        X = parts->xfull;
+        ldx = parts->ld_full;
+    }
     cudaStream_t bm_stream = st;
     if (two) {   // fork: tensor-core hops on the high-priority stream, CSR hops stay on the caller's stream
         H2_CUDA(cudaEventRecord(g->ev_fork, st));
@@ -259,9 +299,11 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
     }
     for (int k = 0; k < g->n_bm; ++k) {
         const int h = g->bm_idx[k];
-        rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X + (x_offsets ? x_offsets[h] : 0), ldx, g->dinv[h], g->xpack,
-                              g->xpack_bytes, (h2_stream_t)bm_stream);
-        if (rc != H2_OK) return rc;
+        if (!(k == 0 && first_bm)) {
+            rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X + (x_offsets ? x_offsets[h] : 0), ldx, g->dinv[h], g->xpack,
+                                  g->xpack_bytes, (h2_stream_t)bm_stream);
+            if (rc != H2_OK) return rc;
+        }
         rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
                             offsets[h], g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
         if (rc != H2_OK) return rc;
@@ -293,6 +335,13 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
                                       (size_t)g->n_rows, cudaMemcpyDeviceToHost, st));
         }
     return H2_OK;
+}
+
+extern "C" int h2_graph_round_parts(h2_graph_t *g, int32_t d, int32_t n_parts, const float *const *part_ptrs_host,
+                                    const int64_t *bounds_host, int64_t ld_part, float *x_full, int64_t ld_full, float *Y,
+                                    int64_t ldy, const int64_t *y_offsets_host, h2_stream_t s) {
+    RoundParts parts{n_parts, part_ptrs_host, bounds_host, ld_part, x_full, ld_full};
+    return graph_round_impl(g, d, nullptr, 0, Y, ldy, y_offsets_host, nullptr, s, nullptr, &parts);
 }
 
 extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,

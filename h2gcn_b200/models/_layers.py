@@ -142,18 +142,23 @@ class GCNLayer(_Named):
     def __init__(self, hops=None):
         self.hops = hops
         self.cpu_large_spmatmul = False
-        self._plans = {}
 
     def selected(self, adjhops):
         return [x for ind, x in enumerate(adjhops) if (self.hops is None or ind in self.hops)]
 
+    # plans are shared by every GCNLayer that aggregates over the same hop tensors (both rounds of H2GCN-2): the
+    # schedule and the tile-bitmap format are built once per graph.  Entries keep the hop tensors alive, so ids stay valid.
+    _shared_plans = {}
+
     def plan_for(self, adjhops):
         sel = self.selected(adjhops)
         key = tuple(id(x) for x in sel)
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = self._plans[key] = ops.HopPlan(sel)
-        return plan
+        entry = GCNLayer._shared_plans.get(key)
+        if entry is None:
+            if len(GCNLayer._shared_plans) >= 16:          # small LRU-less bound: drop the oldest graph
+                GCNLayer._shared_plans.pop(next(iter(GCNLayer._shared_plans)))
+            entry = GCNLayer._shared_plans[key] = (sel, ops.HopPlan(sel))
+        return entry[1]
 
     def sparse_dense_matmul(self, sp_a, b, ind=""):
         """Single-hop product, kept for API parity (_layers.py:62-76)."""

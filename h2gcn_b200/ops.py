@@ -253,6 +253,19 @@ class HopPlan:
         check(lib().h2_graph_round_multi(self._h, d, ptr(x), x.stride(0), xo, ptr(out), out.stride(0), yo, stream_ptr(stream)))
         return out
 
+    def run_parts(self, part_ptrs, bounds, ld_part, x_full, out, offsets, d, stream=None):
+        """Round whose input is given as row shards (device pointers, possibly PEER memory of other ranks): the
+        hop-boundary all-gather happens inside the first kernel of the round (h2_graph_round_parts).  `x_full`
+        [n_cols, d] is scratch for the gathered fp32 copy; the caller brackets the call with cross-rank barriers."""
+        require_cuda(x_full, out)
+        P = len(part_ptrs)
+        ptrs = (ctypes.c_void_p * P)(*part_ptrs)
+        bnd = (ctypes.c_int64 * (P + 1))(*[int(b) for b in bounds])
+        yo = (ctypes.c_int64 * len(offsets))(*offsets)
+        check(lib().h2_graph_round_parts(self._h, d, P, ptrs, bnd, ld_part, ptr(x_full), x_full.stride(0), ptr(out),
+                                         out.stride(0), yo, stream_ptr(stream)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib().h2_graph_destroy(self._h)

@@ -92,7 +92,7 @@ class ShardedGraph:
     equal-rows split and all-gathered (they are also the global degree vector D2 the normalisation needs), the
     nnz-balanced boundaries are derived from them, then every rank fills and normalises its own rows."""
 
-    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=2):
+    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=2, exchange="auto"):
         from . import ops
         self.rank, self.world, self.device, self.group = rank, world, device, group
         a = adj_scipy.tocsr()
@@ -130,6 +130,32 @@ class ShardedGraph:
         self.max_row_nnz = int(max(int(deg1[b:e].max().item()) if self.n_local else 0,
                                    int(deg2[b:e].max().item()) if self.n_local else 0))
         self._x_full = {}
+        # hop-boundary exchange: "p2p" = the ranks' input shards live in symmetric memory and the first kernel of the
+        # round loads them over NVLink (all-gather fused into the pack kernel); "nccl" = ncclAllGather, then the round
+        self.exchange = "nccl"
+        self._sym = {}
+        if world > 1 and exchange in ("auto", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm_mem = symm_mem
+                self.input_buffer(4)            # probe: allocation + rendezvous must work on this box
+                self._sym.clear()
+                self.exchange = "p2p"
+            except Exception as e:              # pragma: no cover - depends on the box
+                if exchange == "p2p":
+                    raise
+                self._exchange_error = repr(e)
+
+    def input_buffer(self, d):
+        """The rank's input shard [n_local, d] for width d, allocated in symmetric memory (peers map it over NVLink).
+        Writing the round input here makes `round` zero-copy; any other tensor is copied in first."""
+        buf = self._sym.get(d)
+        if buf is None:
+            rows = int(np.diff(self.bounds).max())
+            t = self._symm_mem.empty((rows, d), dtype=torch.float32, device=self.device)
+            hdl = self._symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            buf = self._sym[d] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
+        return buf[0][:self.n_local]
 
     def gathered_input(self, x_local):
         """All-gather of the round input at the hop boundary (the one collective of the path)."""
@@ -143,8 +169,22 @@ class ShardedGraph:
 
     def round(self, x_local, y_local, offsets, d=None):
         """y_local[:, offsets[h] : +d] = A_h[local rows, :] @ X  with X = all-gather of the ranks' x_local."""
-        x = self.gathered_input(x_local)
-        return self.plan.run(x, y_local, offsets, d=d)
+        d = x_local.shape[1] if d is None else d
+        if self.world == 1 or self.exchange != "p2p":
+            x = self.gathered_input(x_local)
+            return self.plan.run(x, y_local, offsets, d=d)
+        mine = self.input_buffer(x_local.shape[1])
+        if mine.data_ptr() != x_local.data_ptr():
+            mine.copy_(x_local)
+        t, hdl, ptrs = self._sym[x_local.shape[1]]
+        key = ("full", x_local.shape[1])
+        xf = self._x_full.get(key)
+        if xf is None:
+            xf = self._x_full[key] = torch.empty(self.n, x_local.shape[1], dtype=torch.float32, device=self.device)
+        hdl.barrier(channel=0)          # every rank's shard is written
+        self.plan.run_parts(ptrs, self.bounds, t.stride(0), xf, y_local, offsets, d)
+        hdl.barrier(channel=1)          # every rank has finished reading the shards
+        return y_local
 
     def hops_host(self):
         return [(h.rowptr.cpu().numpy(), h.col.cpu().numpy(), h.values.cpu().numpy()) for h in self.hops]

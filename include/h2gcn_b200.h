@@ -191,6 +191,14 @@ int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float 
 /* backward-style round: hop h reads X[:, x_offsets[h] : +d] (its own slice) and writes Y[:, y_offsets[h] : +d]. */
 int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, const int64_t *x_offsets_host, float *Y,
                          int64_t ldy, const int64_t *y_offsets_host, h2_stream_t s);
+/* Multi-GPU round with the hop-boundary all-gather FUSED into the first consumer: the round input is given
+ * as n_parts (<= 8) row shards — part q holds rows [bounds[q], bounds[q+1]) at part_ptrs[q] (row-major, ld_part) — which
+ * may be PEER pointers (NVLink P2P / symmetric memory).  The pack kernel of the first tensor-core hop (or a plain gather
+ * kernel when every hop is CSR) loads the shards directly over NVLink and also writes the gathered fp32 copy
+ * x_full [n_cols, d] (caller scratch) that CSR hops read.  The caller provides the cross-rank barriers around the call. */
+int h2_graph_round_parts(h2_graph_t *g, int32_t d, int32_t n_parts, const float *const *part_ptrs_host,
+                         const int64_t *bounds_host, int64_t ld_part, float *x_full, int64_t ld_full, float *Y, int64_t ldy,
+                         const int64_t *y_offsets_host, h2_stream_t s);
 /* G[:, 0:d] (+)= sum_s T[:, s*d : (s+1)*d], optionally masked by (mask_src > 0) (ReLU gradient).  accumulate != 0: add to G. */
 int h2_sum_slices_f32(int32_t n_rows, int32_t d, int32_t n_slices, const float *T, int64_t ldt, float *G, int64_t ldg,
                       int32_t accumulate, const float *mask_src, int64_t ld_mask, h2_stream_t s);
