@@ -25,6 +25,8 @@ E_PER_GPU = 200_000
 FEAT = 128
 L2_FLUSH_BYTES = 256 << 20
 L2_BYTES = 126 << 20
+DEFAULT_SPLITS = "2"       # arithmetic of the tensor-core path the headline is measured with
+TRAFFIC_SPLITS = 2         # profiles/traffic.json was captured for this configuration
 
 
 def peaks():
@@ -91,13 +93,18 @@ def build_workload(n, n_edges, seed):
     return synth.uniform_graph(n, n_edges, seed=seed)
 
 
-def cpu_baseline(hops_host, x, budget_s=10.0, min_rounds=3):
-    """Oracle C restatement (OpenMP over rows, every host thread) on full rounds of the SAME workload."""
+def cpu_baseline(hops_host, x, budget_s=10.0, min_rounds=3, y_gpu=None):
+    """Oracle C restatement (OpenMP over rows, every host thread) on full rounds of the SAME workload.  With `y_gpu`
+    (the timed path's output for the same input) it also reports the parity of the measured configuration."""
     from oracle import cbind  # the one place bench.py may run oracle/ (cpu_baseline / --impl reference)
     (rp1, c1, v1), (rp2, c2, v2) = hops_host
     n, d = x.shape
     y = np.empty((n, 2 * d), dtype=np.float32)
     cbind.fused_round(rp1, c1, v1, rp2, c2, v2, x, y)  # warm-up
+    parity = None
+    if y_gpu is not None:
+        parity = {"max_abs_err_over_max_abs_ref": float(np.abs(y_gpu.astype(np.float64) - y).max() / np.abs(y).max()),
+                  "tolerance": 1e-4, "against": "oracle C port (in-order fp32), same input, full output"}
     rounds, t0 = 0, time.perf_counter()
     while rounds < min_rounds or time.perf_counter() - t0 < budget_s:
         cbind.fused_round(rp1, c1, v1, rp2, c2, v2, x, y)
@@ -106,7 +113,8 @@ def cpu_baseline(hops_host, x, budget_s=10.0, min_rounds=3):
     nnz = len(c1) + len(c2)
     return {"value": nnz * d * rounds / dt, "unit": "edges*featdim/s", "cores": cbind.max_threads(), "kind": "port",
             "sample": f"{rounds} full fused rounds of the same workload in {dt:.1f} s (C restatement of the TF-CPU "
-                      f"functor, OpenMP over rows; TensorFlow is not installable here)", "ms_per_round": 1e3 * dt / rounds}
+                      f"functor, OpenMP over rows; TensorFlow is not installable here)", "ms_per_round": 1e3 * dt / rounds,
+            "parity_of_timed_path": parity}
 
 
 def run_reference(args):
@@ -161,8 +169,10 @@ def main():
                     help="hop storage: auto = by density (dense-ish hops on tcgen05), csr = fp32 gather everywhere")
     ap.add_argument("--streams", type=int, default=2, help="caller streams the independent steps are issued on (round-robin)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="N>1: hop-boundary exchange (p2p = fused into the pack kernel over peer memory)")
-    ap.add_argument("--splits", type=int, default=2, help="bf16 pieces of X on the tensor-core path (2 or 3)")
+    ap.add_argument("--splits", default=DEFAULT_SPLITS, help="arithmetic of the tensor-core path: 2 | 3 (bf16 pieces), i8x2 | i8x3 "
+                    "(int8 digits with per-4-row block exponents, exact int32 accumulation)")
     args = ap.parse_args()
+    args.splits = int(args.splits) if str(args.splits).isdigit() else args.splits
     if args.impl == "reference":
         return run_reference(args)
 
@@ -340,7 +350,7 @@ def main():
     achieved = balg / (kern_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and world == 1 and args.mode == "auto" and args.splits == 2:   # measured for this configuration only
+    if os.path.exists(tp) and world == 1 and args.mode == "auto" and args.splits == TRAFFIC_SPLITS:   # measured for this configuration only
         traffic = json.load(open(tp)).get("fused_round_dram_bytes_per_launch")
     line = {
         "metric": "edges*featdim/sec on fused 2-hop SpMM", "value": value, "unit": "edges*featdim/s",
@@ -372,7 +382,8 @@ def main():
     if precompute is not None:
         line["config"]["precompute"] = precompute
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(g.hops_host(), x_full)
+        line["cpu_baseline"] = cpu_baseline(g.hops_host(), x_full, y_gpu=y.cpu().numpy())
+        line["config"]["parity"] = line["cpu_baseline"].pop("parity_of_timed_path")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -14,6 +14,21 @@ H2_OK, H2_ERR_INVALID, H2_ERR_ALIGN, H2_ERR_WORKSPACE, H2_ERR_CUDA, H2_ERR_UNSUP
 
 c_i32, c_i64, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
 
+# `splits` codes of the tensor-core path (include/h2gcn_b200.h): 2 / 3 bf16 pieces, or int8 digits
+H2_SPLITS_I8X2, H2_SPLITS_I8X3 = 18, 19
+SPLITS = {2: 2, 3: 3, "bf16x2": 2, "bf16x3": 3, "i8x2": H2_SPLITS_I8X2, "i8x3": H2_SPLITS_I8X3,
+          H2_SPLITS_I8X2: H2_SPLITS_I8X2, H2_SPLITS_I8X3: H2_SPLITS_I8X3}
+SPLITS_NAME = {2: "2 bf16 pieces", 3: "3 bf16 pieces", H2_SPLITS_I8X2: "2 int8 digits + block exponents",
+               H2_SPLITS_I8X3: "3 int8 digits + block exponents"}
+
+
+def splits_code(splits):
+    """Arithmetic of the tensor-core path: 2 | 3 | "bf16x2" | "bf16x3" | "i8x2" | "i8x3" -> the C-ABI code."""
+    try:
+        return SPLITS[splits]
+    except (KeyError, TypeError):
+        raise ValueError(f"unknown splits {splits!r}: one of 2, 3, 'bf16x2', 'bf16x3', 'i8x2', 'i8x3'")
+
 
 class HopDesc(ctypes.Structure):
     """h2_hop_t"""
@@ -46,6 +61,7 @@ PROTOTYPES = {
     "h2_bm_count": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, ctypes.POINTER(c_i64), c_vp]),
     "h2_bm_plan_dev_bytes": (c_sz, [c_i32, c_i32, c_i64]),
     "h2_bm_fill": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "h2_bm_fill_order": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_i32, c_vp]),
     "h2_bm_xpack_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "h2_bm_partial_bytes": (c_sz, [c_vp, c_i32, c_i32]),
     "h2_bm_pack_x_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -49,7 +49,27 @@ constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in sh
 constexpr int kProducerSets = 1;  // sets of 8 A-producer/epilogue warps taking alternate units (1 keeps the register
                                   // footprint small enough for a CSR-gather CTA of the same round to share the SM)
 constexpr int kBmThreads = (8 * kProducerSets + 2) * 32;   // producer warps, then the TMA warp, then the MMA warp (last)
-constexpr uint32_t kBmMagic = 0x48324232u;  // "H2B2"
+constexpr uint32_t kBmMagic = 0x48324233u;  // "H2B3"
+constexpr int kAStagesMax = 8;   // int8 A tiles are half as wide: up to 8 stages of 32 TMEM columns
+
+// `splits` codes (include/h2gcn_b200.h): 2 / 3 = bf16 pieces; H2_SPLITS_I8X2 / H2_SPLITS_I8X3 = int8 digits with
+// per-4-row block exponents (kind::i8, exact int32 accumulation)
+__host__ __device__ constexpr bool splits_valid(int s) { return s == 2 || s == 3 || s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
+__host__ __device__ constexpr bool splits_i8(int s) { return s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
+__host__ __device__ constexpr int splits_pieces(int s) { return s == H2_SPLITS_I8X2 ? 2 : (s == H2_SPLITS_I8X3 ? 3 : s); }
+// largest magnitude S balanced base-256 digits in [-128, 127] can carry on both signs: 127 * (256^S - 1) / 255
+__host__ __device__ constexpr int i8_range(int S) { return S == 2 ? 32639 : 8355711; }
+constexpr int kI8Levels = 6;          // block exponents t in 0..6: the A operand carries 2^t (<= 64) instead of 1
+constexpr int kI8ConstBytes = 128;    // per B tile: 16 x {rotate amount, byte mask} for the A producers
+constexpr int kI8HeaderBytes = 256;   // xpack header: fp32 quantisation step
+constexpr int kAbsmaxRows = 32;       // rows per CTA of bm_absmax_kernel (8 warps x 4 rows)
+
+// Bit position of column c (0..63) of a unit row.  Order 0: natural.  Order 1 (int8 path): the four columns of an
+// operand word sit 8 bits apart, so that word j = 4 bytes {0, 2^t} comes out of ONE rotate + ONE mask:
+//   bit(c) = 32 * (c / 32) + 8 * (c % 4) + (c % 32) / 4
+__host__ __device__ constexpr int bm_bit_pos(int c, int order) {
+    return order == 0 ? c : 32 * (c / 32) + 8 * (c % 4) + (c % 32) / 4;
+}
 
 struct BmSegment {       // one contiguous run of units inside one (row tile, column group), handled by one CTA
     int32_t tile;
@@ -76,6 +96,7 @@ struct BmSched {
 struct BmHost {          // host header (caller's bm_host buffer)
     uint32_t magic;
     int32_t n_rows, n_cols, n_tiles, n_chunks;
+    int32_t bit_order;   // bm_bit_pos order of the stored bitmaps: 0 (bf16 kernel) / 1 (int8 kernel)
     int64_t n_units;
     int64_t nnz;
     // offsets (bytes) into the device plan buffer
@@ -98,7 +119,7 @@ __global__ void bm_flag_kernel(int32_t n_rows, int32_t n_chunks, const int64_t *
 
 __global__ void bm_fill_kernel(int32_t n_rows, int32_t n_chunks, const int64_t *__restrict__ rowptr,
                                const int32_t *__restrict__ col, const int64_t *__restrict__ unit_index,
-                               int32_t *__restrict__ unit_chunk, unsigned long long *__restrict__ bits) {
+                               int32_t *__restrict__ unit_chunk, unsigned long long *__restrict__ bits, int bit_order) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= n_rows) return;
@@ -109,7 +130,7 @@ __global__ void bm_fill_kernel(int32_t n_rows, int32_t n_chunks, const int64_t *
         const int c = col[k];
         const int chunk = c / kChunkCols;
         const int64_t u = unit_index[base + chunk];
-        atomicOr(&bits[u * kTileRows + r], 1ull << (c % kChunkCols));
+        atomicOr(&bits[u * kTileRows + r], 1ull << bm_bit_pos(c % kChunkCols, bit_order));
         unit_chunk[u] = chunk;  // same value from every writer
     }
 }
@@ -205,6 +226,131 @@ __global__ void gather_rows_kernel(int32_t n_cols, int32_t d4, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// int8 operand (kind::i8): X' = diag(dinv) X as block-fixed-point.
+//   x'[j][c] ~= step * 2^t(j/4) * q[j][c],   q an integer of S balanced base-256 digits (|q| <= i8_range(S)),
+//   step = 2^(e_max - 5) / i8_range(S) for the whole matrix (e_max = exponent of max |x'|), t = block exponent of the
+//   4-row group in 0..6 (groups more than 64x below the maximum keep t = 0 and lose precision gracefully).
+// The 0/1 pattern operand carries 2^t (bm_mma_kernel expands bit -> byte 0 / 2^t), the digits are the int8 B operand,
+// the int32 accumulation is exact, and the epilogue applies step * dinv_row once.
+// Pass 1 (bm_absmax_kernel): max |x'| per 4-row group and per CTA (no atomics: deterministic, nothing to reset);
+// also writes the gathered fp32 copy when the input comes as row shards.  Pass 2 (bm_pack_i8_kernel): quantise and
+// write, per 64-row chunk and column group, the K-major SWIZZLE_64B image of the [S*DG x 64] int8 B tile followed by
+// the 16 {rotate, mask} pairs the A producers need for that chunk.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bm_absmax_kernel(int32_t n_cols, int32_t d, const __grid_constant__ PackSrc src,
+                                                        const float *__restrict__ dinv, float *__restrict__ gmax4,
+                                                        float *__restrict__ blockmax, float *__restrict__ xfull,
+                                                        int64_t ld_full) {
+    __shared__ float s_m[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g4 = blockIdx.x * 8 + warp;          // group of 4 rows
+    const int d4 = d >> 2;
+    float m = 0.f;
+    for (int idx = lane; idx < 4 * d4; idx += 32) {
+        const int j = g4 * 4 + idx / d4, c = idx % d4;
+        if (j < n_cols) {
+            const float4 v = reinterpret_cast<const float4 *>(pack_src_row(src, j))[c];   // plain load: may be peer memory
+            if (xfull) reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full)[c] = v;
+            const float sc = dinv ? __ldg(dinv + j) : 1.f;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x * sc), fabsf(v.y * sc)), fmaxf(fabsf(v.z * sc), fabsf(v.w * sc))));
+        }
+    }
+    m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // non-negative floats order like their bits
+    if (lane == 0) {
+        if (g4 * 4 < n_cols) gmax4[g4] = m;
+        s_m[warp] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = s_m[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) b = fmaxf(b, s_m[w]);
+        blockmax[blockIdx.x] = b;
+    }
+}
+
+__device__ __forceinline__ int f32_exponent(float x) { return (int)((__float_as_uint(x) >> 23) & 0xFFu) - 127; }
+
+template <int DG, int S>
+__global__ void __launch_bounds__(256) bm_pack_i8_kernel(int32_t n_cols, int32_t d, int32_t n_groups,
+                                                         const __grid_constant__ PackSrc src, const float *__restrict__ dinv,
+                                                         const float *__restrict__ gmax4, const float *__restrict__ blockmax,
+                                                         int32_t n_blocks, uint8_t *__restrict__ xpack) {
+    constexpr int NB = S * DG;
+    constexpr int kTileBytes = NB * 64 + kI8ConstBytes;
+    extern __shared__ float s_x[];   // [64][W + 1]
+    __shared__ float s_red[8];
+    __shared__ int s_t[16];
+    const int W = n_groups * DG, ldw = W + 1;
+    const int chunk = blockIdx.x, j0 = chunk * kChunkCols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // global maximum = max over the CTA maxima of pass 1
+    float gm = 0.f;
+    for (int i = threadIdx.x; i < n_blocks; i += 256) gm = fmaxf(gm, blockmax[i]);
+    gm = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gm)));
+    if (lane == 0) s_red[warp] = gm;
+    // the [64 x W] slab scaled by dinv (coalesced 128-bit loads), zero padded
+    const int W4 = W >> 2;
+    for (int idx = threadIdx.x; idx < kChunkCols * W4; idx += 256) {
+        const int k = idx / W4, f4 = (idx % W4) * 4;
+        const int j = j0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n_cols && f4 < d) {
+            v = *reinterpret_cast<const float4 *>(pack_src_row(src, j) + f4);
+            const float sc = dinv ? __ldg(dinv + j) : 1.f;
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        }
+        float *dst = s_x + k * ldw + f4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    gm = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, s_red[w]);
+    const int eg = gm > 0.f ? max(f32_exponent(gm), -96) : -96;
+    if (threadIdx.x < 16) {
+        const int g4 = chunk * 16 + threadIdx.x;
+        const float mg = (g4 * 4 < n_cols) ? gmax4[g4] : 0.f;
+        const int t = mg > 0.f ? min(max(f32_exponent(mg) - eg + kI8Levels, 0), kI8Levels) : 0;
+        s_t[threadIdx.x] = t;
+        // word j of an A row = columns 4j..4j+3 = bits 8k + (j % 8) of half j / 8 (bm_bit_pos order 1):
+        // rotate right by (j % 8) - t, keep bit t of every byte
+        const uint2 c = make_uint2((uint32_t)((threadIdx.x & 7) - t) & 31u, 0x01010101u << t);
+        for (int g = 0; g < n_groups; ++g)
+            *reinterpret_cast<uint2 *>(xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes + NB * 64 + threadIdx.x * 8) = c;
+    }
+    if (chunk == 0 && threadIdx.x == 0) *reinterpret_cast<float *>(xpack) = ldexpf(1.f, eg - 5) / (float)i8_range(S);
+    __syncthreads();
+    const float mult = ldexpf((float)i8_range(S), 5 - eg);
+    // item = (feature f, 16 consecutive k): S x 16 bytes
+    for (int idx = threadIdx.x; idx < W * 4; idx += 256) {
+        const int f = idx % W, c16 = idx / W;
+        uint32_t w[S][4];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int k = c16 * 16 + e;
+            const float sc = __int_as_float((127 - s_t[k >> 2]) << 23);   // 2^-t
+            int q = __float2int_rn(s_x[k * ldw + f] * (mult * sc));
+#pragma unroll
+            for (int t = S - 1; t >= 0; --t) {        // piece 0 = most significant digit
+                const int dig = ((q + 128) & 255) - 128;
+                q = (q - dig) >> 8;
+                const uint32_t b = (uint32_t)dig & 0xFFu;
+                if (e & 3) w[t][e >> 2] |= b << (8 * (e & 3)); else w[t][e >> 2] = b;
+            }
+        }
+        const int g = f / DG, fl = f % DG;
+        uint8_t *tile = xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes;
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            const int n = t * DG + fl;
+            const int off = (n >> 3) * 512 + (n & 7) * 64 + ((c16 ^ ((n >> 1) & 3)) << 4);   // SWIZZLE_64B, 512-byte atoms
+            *reinterpret_cast<uint4 *>(tile + off) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // PTX helpers
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,6 +417,20 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same for int8 operands (K = 32 per instruction), exact int32 accumulation
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_64B operand tile: rows of 64 bytes, 8-row atoms of 512 bytes (verified with tools/umma_i8_probe.cu)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 // K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -281,16 +441,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------------------------
 #ifdef H2_BM_TRACE
 __device__ long long g_bm_trace[148 * 32];
-#define BM_TRACE(slot) do { if (slot < 32) g_bm_trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+#define BM_TRACE(slot) do { if (slot < 26) g_bm_trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+// accumulated wait cycles: slots 26 MMA thread on full_a, 27/28/29 producer warp 0 on full_b / empty_a / wait::st,
+// 30 TMA thread on empty_b, 31 units issued
+#define BM_WAIT_BEGIN() const long long bm_w0__ = clock64()
+#define BM_WAIT_END(slot) g_bm_trace[blockIdx.x * 32 + (slot)] += clock64() - bm_w0__
+#define BM_COUNT(slot) g_bm_trace[blockIdx.x * 32 + (slot)] += 1
 #else
 #define BM_TRACE(slot) do { } while (0)
+#define BM_WAIT_BEGIN() do { } while (0)
+#define BM_WAIT_END(slot) do { } while (0)
+#define BM_COUNT(slot) do { } while (0)
 #endif
 struct BmParams {
     const int32_t *unit_chunk;
     const unsigned long long *bits;
     const BmSegment *seg;
     const int32_t *cta_seg_ptr;  // [n_ctas + 1]
-    const uint4 *xpack;          // [n_chunks][n_groups][S*DG x 64] bf16 tiles
+    const uint4 *xpack;          // [n_chunks][n_groups] B tiles: [S*DG x 64] bf16, or int8 + 128 constant bytes
+    const float *xstep;          // int8 path: quantisation step of X' (device scalar written by the pack kernel)
     const float *dinv_row;       // [n_rows] (local rows) or nullptr
     float *Y;                    // + out_col_off applied by the host
     float *partial;              // [n_partial_slots][256][DG]
@@ -298,30 +467,49 @@ struct BmParams {
     int32_t n_rows, d, n_groups, splits;
 };
 
-template <int DG, int S>
+// I8 = false: bf16 pieces (kind::f16, K = 16, A stage = 2 x 32 TMEM columns, B tile rows of 128 bytes, SWIZZLE_128B)
+// I8 = true : int8 digits (kind::i8, K = 32, A stage = 2 x 16 TMEM columns, B tile rows of 64 bytes, SWIZZLE_64B,
+//             followed by the chunk's 16 {rotate, mask} pairs); same warp roles, barriers and schedule.
+template <int DG, int S, bool I8>
+struct BmCfg {
+    static constexpr int NB = S * DG;                                             // UMMA N
+    static constexpr uint32_t kBBytes = I8 ? NB * 64 + kI8ConstBytes : NB * 128;   // bytes per B tile in global memory
+    static constexpr uint32_t kBStride = (kBBytes + 1023u) & ~1023u;              // shared-memory stage stride
+    static constexpr uint32_t kAccCols = 2 * NB;                                  // two 128-row halves
+    static constexpr uint32_t kAHalfCols = I8 ? 16 : 32;                          // TMEM columns of one half of an A stage
+    static constexpr int kAStg = I8 ? ((512 - (int)kAccCols) / 32 >= 8 ? 8 : 4) : kAStages;
+    static constexpr size_t kSmem = (size_t)kBStages * (kBStride + kTileRows * 8) + 8 * 32 * (DG + 4) * 4 + 1024;
+    static_assert(kAccCols + kAStg * 2 * kAHalfCols <= 512 && NB % 16 == 0 && NB >= 16 && NB <= 256, "UMMA N / TMEM budget");
+    static_assert(kAStg <= kAStagesMax && 8 % kAStg == 0, "A stage ring");
+};
+
+template <int DG, int S, bool I8>
 __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
-    constexpr int NB = S * DG;                      // UMMA N
-    constexpr uint32_t kBBytes = NB * 128;
-    constexpr uint32_t kAccCols = 2 * NB;           // two 128-row halves
+    using Cfg = BmCfg<DG, S, I8>;
+    constexpr int NB = Cfg::NB;
+    constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride;
+    constexpr uint32_t kAccCols = Cfg::kAccCols;
     constexpr uint32_t kACol0 = kAccCols;           // A stages follow the accumulators
+    constexpr uint32_t kAHalfCols = Cfg::kAHalfCols, kAStageCols = 2 * kAHalfCols;
+    constexpr int kAStg = Cfg::kAStg;
     constexpr uint32_t kTmemCols = 512;
-    static_assert(kAccCols + kAStages * 64 <= 512 && NB % 16 == 0 && NB >= 16 && NB <= 256, "UMMA N / TMEM budget");
-    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D format (fp32 = 1 / int32 = 2) | A, B format (bf16 = 1 / signed int8 = 1) | N >> 3 | M >> 4
+    constexpr uint32_t kIdesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
-    const uint32_t bits_base = smem_base + kBStages * kBBytes;           // + kBStages x 2 KB unit bitmaps
+    const uint32_t bits_base = smem_base + kBStages * kBStride;          // + kBStages x 2 KB unit bitmaps
     const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_u32(smem_raw)));
     constexpr int kStageStride = DG + 4;   // floats; +4 keeps 16-byte alignment and spreads rows over the banks
     float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_u32(smem_raw)) + kBStages * kTileRows * 8);
-    __shared__ uint64_t s_bar[2 * kAStages + 2 * kBStages + 2];
+    __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStages + 2];
     __shared__ uint32_t s_tmem_base;
     const uint32_t bar_full_a = smem_u32(&s_bar[0]);
-    const uint32_t bar_empty_a = smem_u32(&s_bar[kAStages]);
-    const uint32_t bar_full_b = smem_u32(&s_bar[2 * kAStages]);
-    const uint32_t bar_empty_b = smem_u32(&s_bar[2 * kAStages + kBStages]);
-    const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kAStages + 2 * kBStages]);
-    const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kAStages + 2 * kBStages + 1]);
+    const uint32_t bar_empty_a = smem_u32(&s_bar[kAStg]);
+    const uint32_t bar_full_b = smem_u32(&s_bar[2 * kAStg]);
+    const uint32_t bar_empty_b = smem_u32(&s_bar[2 * kAStg + kBStages]);
+    const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kAStg + 2 * kBStages]);
+    const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kAStg + 2 * kBStages + 1]);
 
     // The issue arbiter favours the highest warp id of a sub-partition: the MMA issuer must not queue behind the
     // (busy-polling) producer warps, so it is the LAST warp of the CTA.
@@ -331,8 +519,11 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     const int n_work = seg_end - seg_begin;
 
     if (threadIdx.x == 0) {
+#ifdef H2_BM_TRACE
+        for (int q = 26; q < 32; ++q) g_bm_trace[blockIdx.x * 32 + q] = 0;
+#endif
         BM_TRACE(0);
-        for (int s = 0; s < kAStages; ++s) {
+        for (int s = 0; s < kAStg; ++s) {
             mbar_init(bar_full_a + 8 * s, 8);    // one arrive per A-producer warp
             mbar_init(bar_empty_a + 8 * s, 1);   // tcgen05.commit
         }
@@ -367,10 +558,10 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                         const int chunk = chunk_next;
                         if (u + 1 < sg.unit_end) chunk_next = p.unit_chunk[u + 1];   // hide the index load behind the wait
                         const uint32_t st = it % kBStages, ph = (it / kBStages) & 1;
-                        mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
+                        { BM_WAIT_BEGIN(); mbar_wait(bar_empty_b + 8 * st, ph ^ 1); BM_WAIT_END(30); }
                         mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kTileRows * 8);
                         const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
-                        bulk_copy_g2s(smem_base + st * kBBytes, src, kBBytes, bar_full_b + 8 * st);
+                        bulk_copy_g2s(smem_base + st * kBStride, src, kBBytes, bar_full_b + 8 * st);
                         bulk_copy_g2s(bits_base + st * (kTileRows * 8), p.bits + (int64_t)u * kTileRows, kTileRows * 8,
                                       bar_full_b + 8 * st);
                     }
@@ -386,19 +577,23 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
             uint32_t it = 0, acc_it = 0;
             auto issue_unit = [&](auto stage_c, uint32_t acc_first) {
                 constexpr uint32_t ST = decltype(stage_c)::value;      // it & 7
-                constexpr uint32_t sa = ST % kAStages, sb = ST % kBStages;
-                static_assert(8 % kAStages == 0 && 8 % kBStages == 0, "stage rings must divide the unroll factor");
+                constexpr uint32_t sa = ST % kAStg, sb = ST % kBStages;
+                static_assert(8 % kAStg == 0 && 8 % kBStages == 0, "stage rings must divide the unroll factor");
                 // full_a implies full_b: the A producers read the unit's bitmap out of the same B stage
-                mbar_wait(bar_full_a + 8 * sa, (it / kAStages) & 1);
+                { BM_WAIT_BEGIN(); mbar_wait(bar_full_a + 8 * sa, (it / kAStg) & 1); BM_WAIT_END(26); BM_COUNT(31); }
                 tc_fence_after();
-                const uint32_t b0 = smem_base + sb * kBBytes;
-                const uint32_t a0 = tmem_base + kACol0 + sa * 64;
+                const uint32_t b0 = smem_base + sb * kBStride;
+                const uint32_t a0 = tmem_base + kACol0 + sa * kAStageCols;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                    for (int k = 0; k < kChunkCols / 16; ++k) {
-                        umma_bf16_ts(tmem_base + half * NB, a0 + half * 32 + k * 8, umma_desc_sw128(b0 + k * 32), kIdesc,
-                                     k > 0 ? 1u : acc_first);
+                    for (int k = 0; k < kChunkCols / (I8 ? 32 : 16); ++k) {   // 32 operand bytes (8 TMEM columns) per step
+                        if constexpr (I8)
+                            umma_i8_ts(tmem_base + half * NB, a0 + half * kAHalfCols + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc,
+                                       k > 0 ? 1u : acc_first);
+                        else
+                            umma_bf16_ts(tmem_base + half * NB, a0 + half * kAHalfCols + k * 8, umma_desc_sw128(b0 + k * 32), kIdesc,
+                                         k > 0 ? 1u : acc_first);
                     }
                 }
                 umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
@@ -452,27 +647,50 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
                     if (kProducerSets > 1 && (int)(it % kProducerSets) != set) continue;
                     const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
+                    if (warp == 0 && lane == 0) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(27); }
                     mbar_wait(bar_full_b + 8 * sb, pb);        // the unit's bitmap rides in the B stage (TMA-prefetched)
                     const unsigned long long bits = bits_gen[sb * kTileRows + r];
-                    // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
-                    uint32_t a[32];
+                    uint32_t a[I8 ? 16 : 32];
+                    if constexpr (I8) {
+                        // word j = columns 4j..4j+3 as bytes 0 / 2^t: the bits sit 8 apart (bm_bit_pos order 1), so a
+                        // rotate brings them to bit t of each byte and a mask keeps them; {rotate, mask} per word ride
+                        // behind the B tile (the block exponent t belongs to the chunk's rows of X').
+                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_u32(smem_raw)) + sb * kBStride + NB * 64);
+                        const uint32_t x0 = (uint32_t)bits, x1 = (uint32_t)(bits >> 32);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t byte = (uint32_t)(bits >> (8 * c)) & 0xFFu;
+                        for (int q = 0; q < 8; ++q) {
+                            const uint4 c = cst[q];
+                            const uint32_t x = q < 4 ? x0 : x1;
+                            a[2 * q] = __funnelshift_r(x, x, c.x) & c.y;
+                            a[2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
+                        }
+                    } else {
+                        // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            a[4 * c + i] = (byte * ((1u << (14 - 2 * i)) | (1u << (29 - 2 * i)))) & 0x40004000u;
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t byte = (uint32_t)(bits >> (8 * c)) & 0xFFu;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                a[4 * c + i] = (byte * ((1u << (14 - 2 * i)) | (1u << (29 - 2 * i)))) & 0x40004000u;
+                        }
                     }
-                    const uint32_t sa = it % kAStages, pa = (it / kAStages) & 1;
+                    const uint32_t sa = it % kAStg, pa = (it / kAStg) & 1;
+                    if (warp == 0 && lane == 0) { BM_WAIT_BEGIN(); mbar_wait(bar_empty_a + 8 * sa, pa ^ 1); BM_WAIT_END(28); }
                     mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
                     if (pending) {
+#ifdef H2_BM_TRACE
+                        const long long w0 = clock64();
+#endif
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_full_a + 8 * pending_sa);
+#ifdef H2_BM_TRACE
+                        if (warp == 0 && lane == 0) g_bm_trace[blockIdx.x * 32 + 29] += clock64() - w0;
+#endif
                     }
                     tc_fence_after();
-                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 64 + half * 32, a);
+                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * kAStageCols + half * kAHalfCols, a);
                     pending = true;
                     pending_sa = sa;
                 }
@@ -489,7 +707,8 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 if (warp == 0 && lane == 0) BM_TRACE(6 + 6 * w);
                 const int64_t grow = (int64_t)sg.tile * kTileRows + r;
                 const bool row_ok = grow < p.n_rows;
-                const float scale = 0.5f * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);   // A holds 2.0, not 1.0
+                // bf16: A holds 2.0, not 1.0; int8: integer accumulators in units of the quantisation step
+                const float scale = (I8 ? __ldg(p.xstep) : 0.5f) * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
                 const int valid_cols = sg.partial_slot < 0 ? min(DG, p.d - g * DG) : DG;
                 const uint32_t t_row = t_lane + half * NB;
                 // TMEM -> registers (lane = row) -> per-warp shared-memory stage; the accumulator is released as soon as
@@ -508,9 +727,17 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                         float *po = &o.x;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float v = __uint_as_float(acc[S - 1][q + e]);
+                            float v;
+                            if constexpr (I8) {   // digits, most significant first: sum_s 256^(S-1-s) * acc_s
+                                v = (float)(int32_t)acc[S - 1][q + e];
+                                float wgt = 256.f;
 #pragma unroll
-                            for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
+                                for (int s = S - 2; s >= 0; --s, wgt *= 256.f) v = fmaf((float)(int32_t)acc[s][q + e], wgt, v);
+                            } else {
+                                v = __uint_as_float(acc[S - 1][q + e]);
+#pragma unroll
+                                for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
+                            }
                             po[e] = v * scale;
                         }
                         *reinterpret_cast<float4 *>(stage + lane * kStageStride + c0 + q) = o;
@@ -595,7 +822,24 @@ static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // column-group width: S*DG is the UMMA N (<= 256), two accumulators of S*DG columns must fit the 512 TMEM columns
 // column groups are rounded up to a power of two (1, 2, 4, 8): one schedule per count; padding groups compute zeros
 static int groups_for(int d, int dg) { int g = (d + dg - 1) / dg, p2 = 1; while (p2 < g) p2 <<= 1; return p2; }
-static int dg_for(int d, int splits) { return (d <= 32 || splits == 3) ? 32 : 64; }
+static int dg_for(int d, int splits) { return (d <= 32 || splits == 3) ? 32 : 64; }   // int8: 64 for both digit counts
+static size_t i8_tile_bytes(int dg, int splits) { return (size_t)splits_pieces(splits) * dg * 64 + kI8ConstBytes; }
+struct I8Layout {   // int8 xpack buffer: header | tiles | gmax4 [ceil(n_cols/4)] | blockmax [n_blocks]
+    int64_t n_chunks, n_groups, n_g4, n_blocks;
+    size_t off_gmax4, off_blockmax, total;
+};
+static I8Layout i8_layout(int32_t n_cols, int32_t d, int32_t splits) {
+    I8Layout L;
+    const int dg = dg_for(d, splits);
+    L.n_chunks = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
+    L.n_groups = groups_for(d, dg);
+    L.n_g4 = ((int64_t)n_cols + 3) / 4;
+    L.n_blocks = ((int64_t)n_cols + kAbsmaxRows - 1) / kAbsmaxRows;
+    L.off_gmax4 = align_up_sz(kI8HeaderBytes + (size_t)(L.n_chunks * L.n_groups) * i8_tile_bytes(dg, splits), 256);
+    L.off_blockmax = L.off_gmax4 + align_up_sz((size_t)L.n_g4 * 4, 256);
+    L.total = L.off_blockmax + align_up_sz((size_t)L.n_blocks * 4, 256) + 256;
+    return L;
+}
 
 }  // namespace h2
 
@@ -647,9 +891,15 @@ extern "C" size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n
 // Phase 2 (SYNCHRONISES): fills the bitmaps and builds the stream-K schedule (segments, partial slots, fix-ups).
 extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
                           int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, h2_stream_t s) {
+    return h2_bm_fill_order(n_rows, n_cols, rowptr, col, index_ws, n_units, bm_host, bm_dev, bm_dev_bytes, 0, s);
+}
+
+extern "C" int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+                                int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, int32_t bit_order,
+                                h2_stream_t s) {
     cudaStream_t st = (cudaStream_t)s;
-    H2_REQUIRE(n_rows > 0 && n_cols > 0 && rowptr && index_ws && bm_host && bm_dev && n_units >= 0, H2_ERR_INVALID,
-               "h2_bm_fill: bad argument");
+    H2_REQUIRE(n_rows > 0 && n_cols > 0 && rowptr && index_ws && bm_host && bm_dev && n_units >= 0 &&
+               (bit_order == 0 || bit_order == 1), H2_ERR_INVALID, "h2_bm_fill: bad argument");
     H2_REQUIRE(bm_dev_bytes >= h2_bm_plan_dev_bytes(n_rows, n_cols, n_units), H2_ERR_WORKSPACE, "h2_bm_fill: plan buffer too small");
     H2_REQUIRE(n_units < 0x7fffffffLL, H2_ERR_UNSUPPORTED, "h2_bm_fill: too many units");
     const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows, nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
@@ -660,6 +910,7 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
     memset(h, 0, sizeof(*h));
     h->magic = kBmMagic;
     h->n_rows = n_rows; h->n_cols = n_cols; h->n_tiles = (int)nt; h->n_chunks = (int)nc; h->n_units = n_units;
+    h->bit_order = bit_order;
     size_t off = 0;
     h->off_unit_chunk = off; off += align_up_sz((size_t)n_units * 4, 256);
     h->off_bits = off;       off += align_up_sz((size_t)n_units * kTileRows * 8, 256);
@@ -669,7 +920,7 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
     if (n_units > 0) {
         bm_fill_kernel<<<(unsigned)(((int64_t)n_rows * 32 + 255) / 256), 256, 0, st>>>(
             n_rows, (int)nc, rowptr, col, unit_index, (int32_t *)(base + h->off_unit_chunk),
-            (unsigned long long *)(base + h->off_bits));
+            (unsigned long long *)(base + h->off_bits), bit_order);
         H2_LAUNCHED("bm_fill_kernel");
     }
     bm_tile_ptr_kernel<<<(unsigned)((nt + 1 + 255) / 256), 256, 0, st>>>((int)nt, (int)nc, unit_index, tile_ptr_dev);
@@ -756,6 +1007,8 @@ extern "C" int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr,
 static int sched_index(int n_groups) { return n_groups <= 1 ? 0 : (n_groups == 2 ? 1 : (n_groups <= 4 ? 2 : 3)); }
 
 extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
+    if (!splits_valid(splits) || n_cols <= 0 || d <= 0) return 0;
+    if (splits_i8(splits)) return i8_layout(n_cols, d, splits).total;
     const int dg = dg_for(d, splits);
     const int64_t nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols, ng = groups_for(d, dg);
     return (size_t)(nc * ng * splits * dg * 128) + 256;
@@ -763,7 +1016,7 @@ extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
 
 extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits) {
     const BmHost *h = (const BmHost *)bm_host;
-    if (!h || h->magic != kBmMagic) return 0;
+    if (!h || h->magic != kBmMagic || !splits_valid(splits)) return 0;
     const int dg = dg_for(d, splits);
     const int ng = groups_for(d, dg);
     if (ng > 8) return 0;
@@ -790,7 +1043,7 @@ static int fill_src(PackSrc &src, int32_t n_cols, int32_t n_parts, const float *
 int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
                   int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
                   h2_stream_t s) {
-    H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && (splits == 2 || splits == 3) && xpack && ld >= d && ld % 4 == 0,
+    H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && splits_valid(splits) && xpack && ld >= d && ld % 4 == 0,
                H2_ERR_INVALID, "bm_pack: bad argument (d=%d splits=%d)", d, splits);
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
                "bm_pack: xpack buffer too small / misaligned");
@@ -801,6 +1054,35 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
     const int dg = dg_for(d, splits);
     dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for(d, dg));
     cudaStream_t st = (cudaStream_t)s;
+    if (splits_i8(splits)) {
+        // pass 1: maxima (+ the gathered fp32 copy); pass 2: quantise from the local copy when there is one
+        const I8Layout L = i8_layout(n_cols, d, splits);
+        H2_REQUIRE(grid.y <= 8, H2_ERR_UNSUPPORTED, "bm_pack: d=%d needs %u column groups (max 8)", d, grid.y);
+        uint8_t *xp = (uint8_t *)xpack;
+        float *gmax4 = (float *)(xp + L.off_gmax4), *blockmax = (float *)(xp + L.off_blockmax);
+        bm_absmax_kernel<<<(unsigned)L.n_blocks, 256, 0, st>>>(n_cols, d, src, dinv_col, gmax4, blockmax, xfull, ld_full);
+        H2_LAUNCHED("bm_absmax_kernel");
+        PackSrc src2 = src;
+        if (xfull) {
+            const float *one = xfull;
+            const int64_t b2[2] = {0, n_cols};
+            rc = fill_src(src2, n_cols, 1, &one, b2, ld_full);
+            if (rc != H2_OK) return rc;
+        }
+        const size_t smem = (size_t)kChunkCols * (grid.y * dg + 1) * 4;
+        const int S = splits_pieces(splits);
+#define H2_PACK_I8(DG_, S_)                                                                                                 \
+        do {                                                                                                                \
+            auto kern = bm_pack_i8_kernel<DG_, S_>;                                                                         \
+            H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+            kern<<<grid.x, 256, smem, st>>>(n_cols, d, (int)grid.y, src2, dinv_col, gmax4, blockmax, (int)L.n_blocks, xp);  \
+        } while (0)
+        if (dg == 32) { if (S == 2) H2_PACK_I8(32, 2); else H2_PACK_I8(32, 3); }
+        else { if (S == 2) H2_PACK_I8(64, 2); else H2_PACK_I8(64, 3); }
+#undef H2_PACK_I8
+        H2_LAUNCHED("bm_pack_i8_kernel");
+        return H2_OK;
+    }
     if (dg == 32) bm_pack_kernel<32><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, src, dinv_col, (uint4 *)xpack, xfull, ld_full);
     else bm_pack_kernel<64><<<grid, 256, 0, st>>>(n_cols, d, grid.y, splits, src, dinv_col, (uint4 *)xpack, xfull, ld_full);
     H2_LAUNCHED("bm_pack_kernel");
@@ -830,10 +1112,10 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
     return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s);
 }
 
-template <int DG, int S>
+template <int DG, int S, bool I8 = false>
 static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kBStages * (S * DG * 128 + kTileRows * 8) + 8 * 32 * (DG + 4) * 4 + 1024;
-    auto kern = bm_mma_kernel<DG, S>;
+    constexpr size_t smem = BmCfg<DG, S, I8>::kSmem;
+    auto kern = bm_mma_kernel<DG, S, I8>;
     H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sc.n_ctas, kBmThreads, smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
@@ -854,7 +1136,11 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     H2_REQUIRE(d > 0 && d % 4 == 0 && ldy % 4 == 0 && out_col_off % 4 == 0 && out_col_off >= 0 && out_col_off + d <= ldy &&
                aligned16(Y) && aligned16(xpack), H2_ERR_ALIGN, "h2_bm_spmm_f32: d=%d ldy=%lld off=%lld alignment", d,
                (long long)ldy, (long long)out_col_off);
-    H2_REQUIRE(splits == 2 || splits == 3, H2_ERR_INVALID, "h2_bm_spmm_f32: splits must be 2 or 3");
+    H2_REQUIRE(splits_valid(splits), H2_ERR_INVALID, "h2_bm_spmm_f32: splits must be 2, 3, H2_SPLITS_I8X2 or H2_SPLITS_I8X3");
+    const bool i8 = splits_i8(splits);
+    H2_REQUIRE(h->bit_order == (i8 ? 1 : 0), H2_ERR_INVALID, "h2_bm_spmm_f32: plan was filled with bit order %d, splits=%d needs %d "
+               "(h2_bm_fill_order)", h->bit_order, splits, i8 ? 1 : 0);
+    H2_REQUIRE(!i8 || h->n_cols <= (1 << 18), H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: int8 digits need n_cols <= 2^18 (int32 accumulators)");
     const int dg = dg_for(d, splits);
     const int n_groups = groups_for(d, dg);
     H2_REQUIRE(n_groups <= 8, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups (max 8): split the columns", d, n_groups);
@@ -867,7 +1153,8 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     p.bits = (const unsigned long long *)(base + h->off_bits);
     p.seg = (const BmSegment *)(base + sc.off_seg);
     p.cta_seg_ptr = (const int32_t *)(base + sc.off_cta_seg_ptr);
-    p.xpack = (const uint4 *)xpack;
+    p.xpack = (const uint4 *)((const char *)xpack + (i8 ? kI8HeaderBytes : 0));
+    p.xstep = (const float *)xpack;
     p.dinv_row = dinv_row;
     p.Y = Y + out_col_off;
     p.partial = (float *)partial_ws;
@@ -878,6 +1165,8 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
         H2_LAUNCHED("bm_zero_tiles_kernel");
     }
     if (sc.n_ctas == 0) return H2_OK;
+    if (splits == H2_SPLITS_I8X2) return dg == 32 ? bm_launch<32, 2, true>(sc, base, p, st) : bm_launch<64, 2, true>(sc, base, p, st);
+    if (splits == H2_SPLITS_I8X3) return dg == 32 ? bm_launch<32, 3, true>(sc, base, p, st) : bm_launch<64, 3, true>(sc, base, p, st);
     if (splits == 2) return dg == 32 ? bm_launch<32, 2>(sc, base, p, st) : bm_launch<64, 2>(sc, base, p, st);
     return bm_launch<32, 3>(sc, base, p, st);
 }

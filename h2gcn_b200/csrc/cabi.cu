@@ -29,6 +29,7 @@ extern "C" int h2_abi_version(void) { return H2_ABI_VERSION; }
 extern "C" const char *h2_last_error(void) { return t_err; }
 extern "C" int64_t h2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+static bool splits_is_i8(int32_t s);
 // ---- host-buffer graph handle ----------------------------------------------------------------------------------
 struct h2_graph {
     int32_t n_rows = 0, n_cols = 0, n_hops = 0, d_max = 0, splits = 2, row_begin = 0;
@@ -104,8 +105,8 @@ static int graph_finish(h2_graph *g, const bool *want_bitmap) {
             rc = dev_alloc(g, &g->bm_dev[h], pb);
             g->bm_host[h].resize(h2_bm_host_bytes());
             if (rc == H2_OK)
-                rc = h2_bm_fill(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, n_units, g->bm_host[h].data(),
-                                g->bm_dev[h], pb, nullptr);
+                rc = h2_bm_fill_order(n_rows, n_cols, g->hops[h].rowptr, g->hops[h].col, iws, n_units, g->bm_host[h].data(),
+                                      g->bm_dev[h], pb, splits_is_i8(g->splits) ? 1 : 0, nullptr);
         }
         cudaFree(iws);
         if (rc) return rc;
@@ -154,7 +155,11 @@ static int graph_reserve(h2_graph *g, int32_t d) {
     return rc;
 }
 
-static bool pick_bitmap(int32_t mode, bool has_dinv, int64_t nnz, int32_t n_rows, int32_t n_cols) {
+static bool splits_ok(int32_t s) { return s == 2 || s == 3 || s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
+static bool splits_is_i8(int32_t s) { return s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
+
+static bool pick_bitmap(int32_t mode, int32_t splits, bool has_dinv, int64_t nnz, int32_t n_rows, int32_t n_cols) {
+    if (splits_is_i8(splits) && n_cols > (1 << 18)) return false;   // int32 accumulators: <= 2^18 terms of |64 * 127|
     const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
     // measured crossover on B200 (d = 128): a 256x64 unit costs ~6.9 ns on the tensor cores, a CSR entry ~41 ps of
     // gather => the bitmap wins above ~170 entries per unit, i.e. ~1 % density
@@ -167,7 +172,7 @@ extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, c
                                int32_t splits, h2_graph_t **out) {
     H2_REQUIRE(out && n_rows >= 0 && n_cols >= 0 && n_hops >= 1 && n_hops <= H2_MAX_HOPS && d_max >= 4 && d_max % 4 == 0,
                H2_ERR_INVALID, "h2_graph_create: n_rows=%d n_cols=%d n_hops=%d d_max=%d", n_rows, n_cols, n_hops, d_max);
-    H2_REQUIRE(rowptr_host && col_host && val_host && mode >= 0 && mode <= 2 && (splits == 2 || splits == 3) &&
+    H2_REQUIRE(rowptr_host && col_host && val_host && mode >= 0 && mode <= 2 && splits_ok(splits) &&
                row_begin >= 0, H2_ERR_INVALID, "h2_graph_create: null argument / bad mode");
     h2_graph *g = new h2_graph();
     g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = 0; g->splits = splits; g->row_begin = row_begin;
@@ -189,7 +194,7 @@ extern "C" int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, c
             e = cudaMemcpy(dv, dinv_host[h], (size_t)n_cols * 4, cudaMemcpyHostToDevice);
         }
         g->dinv[h] = (const float *)dv;
-        want_bitmap[h] = pick_bitmap(mode, has_dinv, nnz, n_rows, n_cols);
+        want_bitmap[h] = pick_bitmap(mode, splits, has_dinv, nnz, n_rows, n_cols);
         if (!want_bitmap[h]) {
             if (!val_host[h] && nnz) { set_error("h2_graph_create: hop %d needs explicit values", h); return fail(H2_ERR_INVALID); }
             if ((rc = dev_alloc(g, &v, (size_t)nnz * 4))) return fail(rc);
@@ -210,7 +215,7 @@ extern "C" int h2_graph_create_device(int32_t n_rows, int32_t n_cols, int32_t n_
                                       const int64_t *nnz_host, int32_t row_begin, int32_t mode, int32_t splits,
                                       h2_graph_t **out) {
     H2_REQUIRE(out && hops && nnz_host && n_rows >= 0 && n_cols >= 0 && n_hops >= 1 && n_hops <= H2_MAX_HOPS && mode >= 0 &&
-               mode <= 2 && (splits == 2 || splits == 3) && row_begin >= 0, H2_ERR_INVALID,
+               mode <= 2 && splits_ok(splits) && row_begin >= 0, H2_ERR_INVALID,
                "h2_graph_create_device: bad argument (n_hops=%d mode=%d splits=%d)", n_hops, mode, splits);
     h2_graph *g = new h2_graph();
     g->n_rows = n_rows; g->n_cols = n_cols; g->n_hops = n_hops; g->d_max = 0; g->splits = splits; g->row_begin = row_begin;
@@ -224,7 +229,7 @@ extern "C" int h2_graph_create_device(int32_t n_rows, int32_t n_cols, int32_t n_
         }
         g->hops[h] = hops[h];
         g->dinv[h] = hops[h].dinv;
-        want_bitmap[h] = pick_bitmap(mode, hops[h].dinv != nullptr, nnz_host[h], n_rows, n_cols);
+        want_bitmap[h] = pick_bitmap(mode, splits, hops[h].dinv != nullptr, nnz_host[h], n_rows, n_cols);
         if (!want_bitmap[h] && hops[h].val) { g->hops[h].dinv = nullptr; g->hops[h].dinv_row = nullptr; }
         if (!want_bitmap[h] && !hops[h].val) g->hops[h].dinv_row = hops[h].dinv + row_begin;
     }

@@ -194,6 +194,7 @@ class HopPlan:
                 raise ValueError("factored mode needs SparseTensor.dinv on every hop")
             if h.row_begin != hops[0].row_begin:
                 raise ValueError("all hops of a round must be the same row shard")
+        splits = _cabi.splits_code(splits)
         self.factored, self.splits = factored, splits
         self.nnz = sum(h.nnz for h in hops)
         H = len(hops)
@@ -214,7 +215,7 @@ class HopPlan:
         self.tensor_idx = [k for k in range(H) if fmt[k] == 1]
         self.csr_idx = [k for k in range(H) if fmt[k] == 0]
         self.kernel_name = " + ".join(
-            (["bm_mma_kernel (tcgen05 tile-bitmap, %d bf16 pieces) x%d" % (splits, len(self.tensor_idx))] if self.tensor_idx else []) +
+            (["bm_mma_kernel (tcgen05 tile-bitmap, %s) x%d" % (_cabi.SPLITS_NAME[splits], len(self.tensor_idx))] if self.tensor_idx else []) +
             (["fused_hops_gather_kernel (CSR gather) over %d hop(s)" % len(self.csr_idx)] if self.csr_idx else []))
 
     def run(self, x, out, offsets, d=None, stream=None):
@@ -347,7 +348,7 @@ class HostGraph:
         self._h = ctypes.c_void_p()
         self.n_rows, self.n_cols, self.n_hops = n_rows, n_cols, H
         check(lib().h2_graph_create(n_rows, n_cols, H, arr(0), arr(1), arr(2), dv, row_begin, d_max, self.MODES[mode],
-                                    splits, ctypes.byref(self._h)))
+                                    _cabi.splits_code(splits), ctypes.byref(self._h)))
 
     def round(self, x_host, y_host, stream=None):
         """x_host [n_cols, d] / y_host [n_rows, H*d]: (pinned) host torch tensors or numpy arrays, fp32, contiguous."""

@@ -134,9 +134,19 @@ int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_dev, int32_t 
  * (GCNLayer.sparse_dense_matmul, h2gcn/models/_layers.py:62-76); results agree with the fp32 CSR path to ~4e-6
  * relative (splits = 2) — inside the 1e-4 north-star tolerance, not bit-identical.
  *
+ * `splits` selects the arithmetic of the tensor-core path:
+ *   2, 3               X' as 2 / 3 bf16 pieces (16 / 24 significand bits), kind::f16, fp32 accumulation;
+ *   H2_SPLITS_I8X2/3   X' as 2 / 3 balanced base-256 int8 digits of a block-fixed-point number (one step for the whole
+ *                      matrix, a power-of-two block exponent 2^t, t in 0..6, per 4 consecutive rows of X' carried by
+ *                      the 0/1 operand as 0/2^t), kind::i8 at twice the bf16 rate, EXACT int32 accumulation, one fp32
+ *                      rounding in the epilogue.  Measured against the fp32 oracle: ~4e-5 of max-abs (I8X2), ~2e-7 (I8X3).
+ *                      The bitmaps of an int8 plan use bit order 1 (h2_bm_fill_order); n_cols <= 2^18.
+ *
  * Build (once per graph, two phases like hop2): h2_bm_count SYNCHRONISES and returns the number of non-empty
  * 256x64 units; the caller allocates h2_bm_plan_dev_bytes(); h2_bm_fill SYNCHRONISES (it builds the stream-K
  * schedule on the host).  `index_ws` (h2_bm_index_bytes) must stay untouched between the two calls. */
+#define H2_SPLITS_I8X2 18
+#define H2_SPLITS_I8X3 19
 size_t h2_bm_host_bytes(void);
 size_t h2_bm_index_bytes(int32_t n_rows, int32_t n_cols);
 int h2_bm_count(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
@@ -144,6 +154,9 @@ int h2_bm_count(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int
 size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n_units);
 int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
                int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, h2_stream_t s);
+/* same with an explicit bitmap bit order: 0 = natural (bf16 `splits`), 1 = int8 `splits` */
+int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
+                     int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, int32_t bit_order, h2_stream_t s);
 /* per round: pack X' once per distinct dinv_col (NULL = no column scaling), then one h2_bm_spmm_f32 per hop. */
 size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits);
 size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits);

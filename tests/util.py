@@ -59,3 +59,27 @@ def rel_err(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     scale = max(np.abs(ref).max(), 1e-30) if ref.size else 1.0
     return float(np.abs(got - ref).max() / scale) if ref.size else 0.0
+
+
+def i8_block_quantize(xs, pieces):
+    """numpy model of the int8 operand format of the tensor-core path (csrc/bitmap_mma.cu, bm_pack_i8_kernel): `xs` =
+    fp32 diag(dinv) X.  Returns (dequantised fp64 matrix, step, block exponents t per 4-row group).  Not part of the
+    reference — it lets a test check the integer pipeline EXACTLY (the int32 accumulation has no rounding)."""
+    xs = np.asarray(xs, dtype=np.float32)
+    n = xs.shape[0]
+    R = {2: 32639, 3: 8355711}[pieces]
+    expo = lambda v: int(np.frexp(np.float32(v))[1]) - 1          # floor(log2 v) for normal fp32 v > 0
+    gm = float(np.abs(xs).max()) if xs.size else 0.0
+    eg = max(expo(gm), -96) if gm > 0 else -96
+    g4 = (n + 3) // 4
+    pad = np.zeros((g4 * 4, xs.shape[1]), dtype=np.float32)
+    pad[:n] = np.abs(xs)
+    mg = pad.reshape(g4, 4, -1).max(axis=(1, 2))
+    t = np.array([min(max(expo(m) - eg + 6, 0), 6) if m > 0 else 0 for m in mg], dtype=np.int64)
+    trow = np.repeat(t, 4)[:n]
+    mult = np.float32(np.ldexp(np.float32(R), 5 - eg))
+    scale = (mult * np.ldexp(np.float32(1), -trow).astype(np.float32)).astype(np.float32)
+    q = np.rint((xs * scale[:, None]).astype(np.float32)).astype(np.int64)
+    assert np.abs(q).max(initial=0) <= R
+    step = np.float32(np.ldexp(np.float32(1), eg - 5) / np.float32(R))
+    return q.astype(np.float64) * np.ldexp(1.0, trow)[:, None] * float(step), float(step), t

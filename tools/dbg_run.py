@@ -8,7 +8,9 @@ from h2gcn_b200.utils import synth
 from h2gcn_b200 import _cabi
 dev = torch.device('cuda:0')
 adj = synth.uniform_graph(10000, 200000, seed=0)
-g = ShardedGraph(adj, 0, 1, dev)
+splits = sys.argv[1] if len(sys.argv) > 1 else "2"
+splits = int(splits) if splits.isdigit() else splits
+g = ShardedGraph(adj, 0, 1, dev, splits=splits)
 x = torch.from_numpy(synth.features(10000, 128, 0)).to(dev); y = torch.empty(10000, 256, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(3):
@@ -19,12 +21,17 @@ buf = np.zeros(148 * 32, dtype=np.int64)
 lib.h2_debug_read(buf.ctypes.data_as(ctypes.c_void_p))
 b = buf.reshape(148, 32)
 dur = b[:, 1] - b[:, 0]
-print("CTA duration cycles: min %d median %d max %d" % (dur.min(), np.median(dur), dur.max()))
+print("splits", splits, "CTA duration cycles: min %d median %d max %d" % (dur.min(), np.median(dur), dur.max()))
+w = b[:, 26:32]
+print("median per CTA: units %d | MMA thread waits full_a %d | producer warp 0 waits full_b %d, empty_a %d, wait::st+arrive %d | "
+      "TMA thread waits empty_b %d" % (np.median(w[:, 5]), np.median(w[:, 0]), np.median(w[:, 1]), np.median(w[:, 2]),
+                                       np.median(w[:, 3]), np.median(w[:, 4])))
 for c in [0, 1, 2, 37, 73, 74, 100, 147]:
     r = b[c]; t0 = r[0]
     segs = []
     for w in range(4):
         s = r[2 + 6 * w: 8 + 6 * w]
+        if 8 + 6 * w > 26: break
         if s[0] == 0: break
         segs.append([int(v - t0) for v in s])
     print(c, "end", int(r[1] - t0), segs)
