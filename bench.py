@@ -25,8 +25,7 @@ E_PER_GPU = 200_000
 FEAT = 128
 L2_FLUSH_BYTES = 256 << 20
 L2_BYTES = 126 << 20
-DEFAULT_SPLITS = "2"       # arithmetic of the tensor-core path the headline is measured with
-TRAFFIC_SPLITS = 2         # profiles/traffic.json was captured for this configuration
+DEFAULT_SPLITS = None      # arithmetic of the tensor-core path: None = the library default (h2gcn_b200._cabi.DEFAULT_SPLITS)
 
 
 def peaks():
@@ -172,7 +171,8 @@ def main():
     ap.add_argument("--splits", default=DEFAULT_SPLITS, help="arithmetic of the tensor-core path: 2 | 3 (bf16 pieces), i8x2 | i8x3 "
                     "(int8 digits with per-4-row block exponents, exact int32 accumulation)")
     args = ap.parse_args()
-    args.splits = int(args.splits) if str(args.splits).isdigit() else args.splits
+    from h2gcn_b200 import _cabi as _c
+    args.splits = _c.splits_code(args.splits)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -350,8 +350,8 @@ def main():
     achieved = balg / (kern_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and world == 1 and args.mode == "auto" and args.splits == TRAFFIC_SPLITS:   # measured for this configuration only
-        traffic = json.load(open(tp)).get("fused_round_dram_bytes_per_launch")
+    if os.path.exists(tp) and world == 1 and args.mode == "auto":   # measured per arithmetic, for this workload only
+        traffic = json.load(open(tp)).get("fused_round_dram_bytes_per_launch", {}).get(_cabi.SPLITS_NAME[args.splits])
     line = {
         "metric": "edges*featdim/sec on fused 2-hop SpMM", "value": value, "unit": "edges*featdim/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

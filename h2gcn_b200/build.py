@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 SO = os.path.join(LIBDIR, "libh2gcn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DH2_BM_TRACE"] if os.environ.get("H2_BM_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+FLAGS = (["-DH2_BM_TRACE"] if os.environ.get("H2_BM_TRACE") else []) + os.environ.get("H2_EXTRA_NVCC_FLAGS", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 

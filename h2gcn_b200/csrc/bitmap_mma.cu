@@ -46,9 +46,13 @@ constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B ti
 constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kAStages = 4;    // A tiles live in TMEM: 4 x (2 halves x 32 columns) next to 2 x 128 accumulator columns
 constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in shared memory
-constexpr int kProducerSets = 1;  // sets of 8 A-producer/epilogue warps taking alternate units (1 keeps the register
-                                  // footprint small enough for a CSR-gather CTA of the same round to share the SM)
-constexpr int kBmThreads = (8 * kProducerSets + 2) * 32;   // producer warps, then the TMA warp, then the MMA warp (last)
+// sets of 8 A-producer/epilogue warps: 1 for the bf16 kernel (keeps the register footprint small enough for a CSR-gather
+// CTA of the same round to share the SM), 2 for the int8 kernel (a unit is half the MMA time: see the producer loop)
+#ifndef H2_BM_I8_SETS
+#define H2_BM_I8_SETS 1
+#endif
+__host__ __device__ constexpr int bm_producer_sets(bool i8) { return i8 ? H2_BM_I8_SETS : 1; }
+__host__ __device__ constexpr int bm_threads(bool i8) { return (8 * bm_producer_sets(i8) + 2) * 32; }   // producers, TMA warp, MMA warp (last)
 constexpr uint32_t kBmMagic = 0x48324233u;  // "H2B3"
 constexpr int kAStagesMax = 8;   // int8 A tiles are half as wide: up to 8 stages of 32 TMEM columns
 
@@ -271,43 +275,44 @@ __global__ void __launch_bounds__(256) bm_absmax_kernel(int32_t n_cols, int32_t 
 
 __device__ __forceinline__ int f32_exponent(float x) { return (int)((__float_as_uint(x) >> 23) & 0xFFu) - 127; }
 
+constexpr int kPackFeat = 32;   // features per CTA of bm_pack_i8_kernel
+
 template <int DG, int S>
-__global__ void __launch_bounds__(256) bm_pack_i8_kernel(int32_t n_cols, int32_t d, int32_t n_groups,
+__global__ void __launch_bounds__(128) bm_pack_i8_kernel(int32_t n_cols, int32_t d, int32_t n_groups,
                                                          const __grid_constant__ PackSrc src, const float *__restrict__ dinv,
                                                          const float *__restrict__ gmax4, const float *__restrict__ blockmax,
                                                          int32_t n_blocks, uint8_t *__restrict__ xpack) {
     constexpr int NB = S * DG;
     constexpr int kTileBytes = NB * 64 + kI8ConstBytes;
-    extern __shared__ float s_x[];   // [64][W + 1]
-    __shared__ float s_red[8];
+    constexpr int kSlices = DG / kPackFeat;           // CTAs per (chunk, column group)
+    __shared__ float s_x[kChunkCols][kPackFeat + 1];
+    __shared__ float s_red[4];
     __shared__ int s_t[16];
-    const int W = n_groups * DG, ldw = W + 1;
     const int chunk = blockIdx.x, j0 = chunk * kChunkCols;
+    const int g = blockIdx.y / kSlices, slice = blockIdx.y % kSlices;
+    const int f0 = g * DG + slice * kPackFeat;        // first feature of this CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // global maximum = max over the CTA maxima of pass 1
     float gm = 0.f;
-    for (int i = threadIdx.x; i < n_blocks; i += 256) gm = fmaxf(gm, blockmax[i]);
+    for (int i = threadIdx.x; i < n_blocks; i += 128) gm = fmaxf(gm, blockmax[i]);
     gm = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gm)));
     if (lane == 0) s_red[warp] = gm;
-    // the [64 x W] slab scaled by dinv (coalesced 128-bit loads), zero padded
-    const int W4 = W >> 2;
-    for (int idx = threadIdx.x; idx < kChunkCols * W4; idx += 256) {
-        const int k = idx / W4, f4 = (idx % W4) * 4;
+    // the [64 x 32] slab scaled by dinv (128-bit loads), zero padded
+    for (int idx = threadIdx.x; idx < kChunkCols * (kPackFeat / 4); idx += 128) {
+        const int k = idx / (kPackFeat / 4), f4 = (idx % (kPackFeat / 4)) * 4;
         const int j = j0 + k;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < n_cols && f4 < d) {
-            v = *reinterpret_cast<const float4 *>(pack_src_row(src, j) + f4);
+        if (j < n_cols && f0 + f4 < d) {
+            v = *reinterpret_cast<const float4 *>(pack_src_row(src, j) + f0 + f4);
             const float sc = dinv ? __ldg(dinv + j) : 1.f;
             v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
         }
-        float *dst = s_x + k * ldw + f4;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        s_x[k][f4] = v.x; s_x[k][f4 + 1] = v.y; s_x[k][f4 + 2] = v.z; s_x[k][f4 + 3] = v.w;
     }
     __syncthreads();
-    gm = s_red[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, s_red[w]);
+    gm = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
     const int eg = gm > 0.f ? max(f32_exponent(gm), -96) : -96;
+    uint8_t *tile = xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes;
     if (threadIdx.x < 16) {
         const int g4 = chunk * 16 + threadIdx.x;
         const float mg = (g4 * 4 < n_cols) ? gmax4[g4] : 0.f;
@@ -315,22 +320,23 @@ __global__ void __launch_bounds__(256) bm_pack_i8_kernel(int32_t n_cols, int32_t
         s_t[threadIdx.x] = t;
         // word j of an A row = columns 4j..4j+3 = bits 8k + (j % 8) of half j / 8 (bm_bit_pos order 1):
         // rotate right by (j % 8) - t, keep bit t of every byte
-        const uint2 c = make_uint2((uint32_t)((threadIdx.x & 7) - t) & 31u, 0x01010101u << t);
-        for (int g = 0; g < n_groups; ++g)
-            *reinterpret_cast<uint2 *>(xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes + NB * 64 + threadIdx.x * 8) = c;
+        if (slice == 0)
+            *reinterpret_cast<uint2 *>(tile + NB * 64 + threadIdx.x * 8) =
+                make_uint2((uint32_t)((threadIdx.x & 7) - t) & 31u, 0x01010101u << t);
     }
-    if (chunk == 0 && threadIdx.x == 0) *reinterpret_cast<float *>(xpack) = ldexpf(1.f, eg - 5) / (float)i8_range(S);
+    if (chunk == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        *reinterpret_cast<float *>(xpack) = ldexpf(1.f, eg - 5) / (float)i8_range(S);
     __syncthreads();
     const float mult = ldexpf((float)i8_range(S), 5 - eg);
-    // item = (feature f, 16 consecutive k): S x 16 bytes
-    for (int idx = threadIdx.x; idx < W * 4; idx += 256) {
-        const int f = idx % W, c16 = idx / W;
+    // thread = (feature fl, 16 consecutive k): S x 16 bytes
+    {
+        const int fl = threadIdx.x % kPackFeat, c16 = threadIdx.x / kPackFeat;
         uint32_t w[S][4];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const int k = c16 * 16 + e;
             const float sc = __int_as_float((127 - s_t[k >> 2]) << 23);   // 2^-t
-            int q = __float2int_rn(s_x[k * ldw + f] * (mult * sc));
+            int q = __float2int_rn(s_x[k][fl] * (mult * sc));
 #pragma unroll
             for (int t = S - 1; t >= 0; --t) {        // piece 0 = most significant digit
                 const int dig = ((q + 128) & 255) - 128;
@@ -339,11 +345,9 @@ __global__ void __launch_bounds__(256) bm_pack_i8_kernel(int32_t n_cols, int32_t
                 if (e & 3) w[t][e >> 2] |= b << (8 * (e & 3)); else w[t][e >> 2] = b;
             }
         }
-        const int g = f / DG, fl = f % DG;
-        uint8_t *tile = xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes;
 #pragma unroll
         for (int t = 0; t < S; ++t) {
-            const int n = t * DG + fl;
+            const int n = t * DG + slice * kPackFeat + fl;
             const int off = (n >> 3) * 512 + (n & 7) * 64 + ((c16 ^ ((n >> 1) & 3)) << 4);   // SWIZZLE_64B, 512-byte atoms
             *reinterpret_cast<uint4 *>(tile + off) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
         }
@@ -387,6 +391,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
+}
+// one attempt, no loop: lets a caller start the (slow, ~200-cycle) phase check of the NEXT unit ahead of time
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -441,17 +456,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------------------------
 #ifdef H2_BM_TRACE
 __device__ long long g_bm_trace[148 * 32];
+__device__ long long g_bm_trace2[8 * 64];   // CTA 0 only, per unit (first 64): see tools/dbg_run.py
 #define BM_TRACE(slot) do { if (slot < 26) g_bm_trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+#define BM_T2(row, unit) do { if (blockIdx.x == 0 && (unit) < 64u) g_bm_trace2[(row) * 64 + (unit)] = clock64(); } while (0)
 // accumulated wait cycles: slots 26 MMA thread on full_a, 27/28/29 producer warp 0 on full_b / empty_a / wait::st,
 // 30 TMA thread on empty_b, 31 units issued
+// (kept in registers, stored once when the role ends)
+#define BM_ACC_DECL() long long bm_acc__[3] = {0, 0, 0}
 #define BM_WAIT_BEGIN() const long long bm_w0__ = clock64()
-#define BM_WAIT_END(slot) g_bm_trace[blockIdx.x * 32 + (slot)] += clock64() - bm_w0__
-#define BM_COUNT(slot) g_bm_trace[blockIdx.x * 32 + (slot)] += 1
+#define BM_WAIT_END(k) bm_acc__[k] += clock64() - bm_w0__
+#define BM_COUNT(k) bm_acc__[k] += 1
+#define BM_ACC_STORE(k, slot) g_bm_trace[blockIdx.x * 32 + (slot)] = bm_acc__[k]
 #else
 #define BM_TRACE(slot) do { } while (0)
+#define BM_T2(row, unit) do { } while (0)
+#define BM_ACC_DECL() do { } while (0)
 #define BM_WAIT_BEGIN() do { } while (0)
-#define BM_WAIT_END(slot) do { } while (0)
-#define BM_COUNT(slot) do { } while (0)
+#define BM_WAIT_END(k) do { } while (0)
+#define BM_COUNT(k) do { } while (0)
+#define BM_ACC_STORE(k, slot) do { } while (0)
 #endif
 struct BmParams {
     const int32_t *unit_chunk;
@@ -484,8 +507,9 @@ struct BmCfg {
 };
 
 template <int DG, int S, bool I8>
-__global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
+__global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
     using Cfg = BmCfg<DG, S, I8>;
+    constexpr int kProducerSets = bm_producer_sets(I8);
     constexpr int NB = Cfg::NB;
     constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride;
     constexpr uint32_t kAccCols = Cfg::kAccCols;
@@ -497,19 +521,27 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     constexpr uint32_t kIdesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
+    // Shared-window addresses are made opaque to the compiler: left alone it REMATERIALISES them inside the unit loops
+    // from S2R SR_CgaCtaId (a long-scoreboard read, measured as 30 % of the A producers' time) instead of keeping them
+    // in a register.
+    uint32_t smem_raw_u32 = smem_u32(smem_raw);
+    asm volatile("" : "+r"(smem_raw_u32));
+    const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;   // B stages, 1024-byte aligned (swizzle atoms)
     const uint32_t bits_base = smem_base + kBStages * kBStride;          // + kBStages x 2 KB unit bitmaps
-    const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_u32(smem_raw)));
+    const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_raw_u32));
     constexpr int kStageStride = DG + 4;   // floats; +4 keeps 16-byte alignment and spreads rows over the banks
-    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_u32(smem_raw)) + kBStages * kTileRows * 8);
+    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kBStages * kTileRows * 8);
     __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStages + 2];
     __shared__ uint32_t s_tmem_base;
-    const uint32_t bar_full_a = smem_u32(&s_bar[0]);
-    const uint32_t bar_empty_a = smem_u32(&s_bar[kAStg]);
-    const uint32_t bar_full_b = smem_u32(&s_bar[2 * kAStg]);
-    const uint32_t bar_empty_b = smem_u32(&s_bar[2 * kAStg + kBStages]);
-    const uint32_t bar_acc_full = smem_u32(&s_bar[2 * kAStg + 2 * kBStages]);
-    const uint32_t bar_acc_empty = smem_u32(&s_bar[2 * kAStg + 2 * kBStages + 1]);
+    __shared__ int s_chunk[32];
+    uint32_t bar0 = smem_u32(&s_bar[0]);
+    asm volatile("" : "+r"(bar0));
+    const uint32_t bar_full_a = bar0;
+    const uint32_t bar_empty_a = bar0 + 8 * kAStg;
+    const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);
+    const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kBStages);
+    const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kBStages);
+    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kBStages + 1);
 
     // The issue arbiter favours the highest warp id of a sub-partition: the MMA issuer must not queue behind the
     // (busy-polling) producer warps, so it is the LAST warp of the CTA.
@@ -519,12 +551,9 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
     const int n_work = seg_end - seg_begin;
 
     if (threadIdx.x == 0) {
-#ifdef H2_BM_TRACE
-        for (int q = 26; q < 32; ++q) g_bm_trace[blockIdx.x * 32 + q] = 0;
-#endif
         BM_TRACE(0);
         for (int s = 0; s < kAStg; ++s) {
-            mbar_init(bar_full_a + 8 * s, 8);    // one arrive per A-producer warp
+            mbar_init(bar_full_a + 8 * s, I8 ? 4 : 8);    // one arrive per A-producer warp of the unit
             mbar_init(bar_empty_a + 8 * s, 1);   // tcgen05.commit
         }
         for (int s = 0; s < kBStages; ++s) {
@@ -547,27 +576,40 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
 
     if (warp == kTmaWarp) {
         // ===== TMA producer (B tiles + unit bitmaps) =====
-        if (elect_one()) {
-            uint32_t it = 0;
-            for (int w = 0; w < n_work; ++w) {
-                const BmSegment sg = p.seg[seg_begin + w];
-                const int g = sg.group;
-                {
-                    int chunk_next = sg.unit_begin < sg.unit_end ? p.unit_chunk[sg.unit_begin] : 0;
-                    for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                        const int chunk = chunk_next;
-                        if (u + 1 < sg.unit_end) chunk_next = p.unit_chunk[u + 1];   // hide the index load behind the wait
-                        const uint32_t st = it % kBStages, ph = (it / kBStages) & 1;
-                        { BM_WAIT_BEGIN(); mbar_wait(bar_empty_b + 8 * st, ph ^ 1); BM_WAIT_END(30); }
+        // The column chunk of every unit comes from global memory: the WHOLE warp fetches 32 indices at a time (one
+        // coalesced load, the next block prefetched while this one is issued) and parks them in shared memory; one
+        // elected lane then issues the copies of those 32 units back to back.  (A single lane loading one index per
+        // unit exposes the load latency whenever it does not have to wait for a free stage: measured ~380 cycles per
+        // unit, more than the 256 cycles of int8 MMA work.)
+        uint32_t it = 0;
+        BM_ACC_DECL();
+        for (int w = 0; w < n_work; ++w) {
+            const BmSegment sg = p.seg[seg_begin + w];
+            const int g = sg.group;
+            int nxt = sg.unit_begin + lane < sg.unit_end ? p.unit_chunk[sg.unit_begin + lane] : 0;
+            for (int u0 = sg.unit_begin; u0 < sg.unit_end; u0 += 32) {
+                s_chunk[lane] = nxt;
+                __syncwarp();
+                if (u0 + 32 + lane < sg.unit_end) nxt = p.unit_chunk[u0 + 32 + lane];
+                const int cnt = min(32, sg.unit_end - u0);
+                if (elect_one()) {
+                    for (int k = 0; k < cnt; ++k) {
+                        const int chunk = s_chunk[k];
+                        const uint32_t st = (it + k) % kBStages, ph = ((it + k) / kBStages) & 1;
+                        { BM_WAIT_BEGIN(); mbar_wait(bar_empty_b + 8 * st, ph ^ 1); BM_WAIT_END(0); }
+                        BM_T2(0, it + k);
                         mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kTileRows * 8);
                         const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
                         bulk_copy_g2s(smem_base + st * kBStride, src, kBBytes, bar_full_b + 8 * st);
-                        bulk_copy_g2s(bits_base + st * (kTileRows * 8), p.bits + (int64_t)u * kTileRows, kTileRows * 8,
+                        bulk_copy_g2s(bits_base + st * (kTileRows * 8), p.bits + (int64_t)(u0 + k) * kTileRows, kTileRows * 8,
                                       bar_full_b + 8 * st);
                     }
                 }
+                it += cnt;
+                __syncwarp();
             }
         }
+        if (lane == 0) BM_ACC_STORE(0, 30);
     } else if (warp == kMmaWarp) {
         // ===== MMA issuer: ONE elected lane runs the whole loop (no per-unit reconvergence).  A single thread executes
         // ~one dependent instruction per 5-10 cycles, so the per-unit instruction count is what bounds the issue rate:
@@ -575,12 +617,14 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
         // TMEM address and barrier address is loop-invariant-base + immediate. =====
         if (elect_one()) {
             uint32_t it = 0, acc_it = 0;
+            BM_ACC_DECL();
             auto issue_unit = [&](auto stage_c, uint32_t acc_first) {
                 constexpr uint32_t ST = decltype(stage_c)::value;      // it & 7
                 constexpr uint32_t sa = ST % kAStg, sb = ST % kBStages;
                 static_assert(8 % kAStg == 0 && 8 % kBStages == 0, "stage rings must divide the unroll factor");
                 // full_a implies full_b: the A producers read the unit's bitmap out of the same B stage
-                { BM_WAIT_BEGIN(); mbar_wait(bar_full_a + 8 * sa, (it / kAStg) & 1); BM_WAIT_END(26); BM_COUNT(31); }
+                { BM_WAIT_BEGIN(); mbar_wait(bar_full_a + 8 * sa, (it / kAStg) & 1); BM_WAIT_END(0); BM_COUNT(1); }
+                BM_T2(5, it);
                 tc_fence_after();
                 const uint32_t b0 = smem_base + sb * kBStride;
                 const uint32_t a0 = tmem_base + kACol0 + sa * kAStageCols;
@@ -598,6 +642,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 }
                 umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
                 umma_commit(bar_empty_b + 8 * sb);
+                BM_T2(6, it);
                 ++it;
             };
             for (int w = 0; w < n_work; ++w) {
@@ -625,6 +670,8 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                     BM_TRACE(4 + 6 * w);
                 }
             }
+            BM_ACC_STORE(0, 26);
+            BM_ACC_STORE(1, 31);
         }
         __syncwarp();
     } else {
@@ -638,33 +685,53 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
         const int r = half * 128 + quarter * 32 + lane;   // row inside the 256-row tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t it = 0, acc_it = 0;
+        BM_ACC_DECL();
         for (int w = 0; w < n_work; ++w) {
             const BmSegment sg = p.seg[seg_begin + w];
             const int g = sg.group;
             for (int once = 0; once < 1; ++once, ++acc_it) {
                 bool pending = false;
                 uint32_t pending_sa = 0;
-                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    if (kProducerSets > 1 && (int)(it % kProducerSets) != set) continue;
+                // bf16: sets of 8 warps (half x quarter) take alternate units.  int8: a unit is only 256 cycles of MMA work
+                // while one warp needs several hundred cycles per unit it expands (a single warp issues one dependent
+                // instruction every ~4.5 cycles, and the phase check of an mbarrier completed by TMA costs ~200), so the
+                // warps are grouped by 4 (one per TMEM lane quarter), group k takes the units with it % kStep == k, a
+                // thread expands BOTH of its rows (lane of half 0 and of half 1: the unit's {rotate, mask} constants are
+                // loaded once for two rows), and the phase check of the group's next unit is started one unit ahead.
+                constexpr int kStep = I8 ? 2 * kProducerSets : kProducerSets;
+                const int mine = I8 ? (pw >> 2) : set;
+                const int skip = (int)((uint32_t)(mine + kStep - (int)(it % kStep)) % kStep);
+                const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
+                it += skip;
+                uint32_t ready = 0;
+                if (I8 && sg.unit_begin + skip < sg.unit_end) ready = mbar_try_wait(bar_full_b + 8 * (it % kBStages), (it / kBStages) & 1);
+                for (int u = sg.unit_begin + skip; u < sg.unit_end; u += kStep, it += kStep) {
                     const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
-                    if (warp == 0 && lane == 0) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(27); }
-                    mbar_wait(bar_full_b + 8 * sb, pb);        // the unit's bitmap rides in the B stage (TMA-prefetched)
-                    const unsigned long long bits = bits_gen[sb * kTileRows + r];
-                    uint32_t a[I8 ? 16 : 32];
+                    // the unit's bitmap rides in the B stage (TMA-prefetched)
+                    if (!I8 || !ready) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(0); }
+                    if ((warp & 3) == 0 && lane == 0) BM_T2(1, it);
+                    uint32_t a[32];
                     if constexpr (I8) {
                         // word j = columns 4j..4j+3 as bytes 0 / 2^t: the bits sit 8 apart (bm_bit_pos order 1), so a
                         // rotate brings them to bit t of each byte and a mask keeps them; {rotate, mask} per word ride
                         // behind the B tile (the block exponent t belongs to the chunk's rows of X').
-                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_u32(smem_raw)) + sb * kBStride + NB * 64);
-                        const uint32_t x0 = (uint32_t)bits, x1 = (uint32_t)(bits >> 32);
+                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NB * 64);
+                        const unsigned long long b0 = bits_gen[sb * kTileRows + quarter * 32 + lane];
+                        const unsigned long long b1 = bits_gen[sb * kTileRows + 128 + quarter * 32 + lane];
+                        const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32), y0 = (uint32_t)b1, y1 = (uint32_t)(b1 >> 32);
+                        if (u + kStep < sg.unit_end)   // start the next unit's phase check behind the expansion below
+                            ready = mbar_try_wait(bar_full_b + 8 * ((it + kStep) % kBStages), ((it + kStep) / kBStages) & 1);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const uint4 c = cst[q];
-                            const uint32_t x = q < 4 ? x0 : x1;
+                            const uint32_t x = q < 4 ? x0 : x1, y = q < 4 ? y0 : y1;
                             a[2 * q] = __funnelshift_r(x, x, c.x) & c.y;
                             a[2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
+                            a[16 + 2 * q] = __funnelshift_r(y, y, c.x) & c.y;       // half 1: the next 16 TMEM columns
+                            a[16 + 2 * q + 1] = __funnelshift_r(y, y, c.z) & c.w;
                         }
                     } else {
+                        const unsigned long long bits = bits_gen[sb * kTileRows + r];
                         // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -675,25 +742,24 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                         }
                     }
                     const uint32_t sa = it % kAStg, pa = (it / kAStg) & 1;
-                    if (warp == 0 && lane == 0) { BM_WAIT_BEGIN(); mbar_wait(bar_empty_a + 8 * sa, pa ^ 1); BM_WAIT_END(28); }
-                    mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
-                    if (pending) {
-#ifdef H2_BM_TRACE
-                        const long long w0 = clock64();
-#endif
+                    if ((warp & 3) == 0 && lane == 0) BM_T2(2, it);
+                    if (pending) {   // publish the previous unit BEFORE waiting for a free stage (it may be the same stage)
+                        BM_WAIT_BEGIN();
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_full_a + 8 * pending_sa);
-#ifdef H2_BM_TRACE
-                        if (warp == 0 && lane == 0) g_bm_trace[blockIdx.x * 32 + 29] += clock64() - w0;
-#endif
+                        BM_WAIT_END(2);
                     }
+                    { BM_WAIT_BEGIN(); mbar_wait(bar_empty_a + 8 * sa, pa ^ 1); BM_WAIT_END(1); }
+                    if ((warp & 3) == 0 && lane == 0) BM_T2(3, it);
                     tc_fence_after();
-                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * kAStageCols + half * kAHalfCols, a);
+                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * kAStageCols + (I8 ? 0 : half * kAHalfCols), a);
+                    if ((warp & 3) == 0 && lane == 0) BM_T2(4, it);
                     pending = true;
                     pending_sa = sa;
                 }
+                it = it_end;
                 if (pending) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
@@ -765,6 +831,7 @@ __global__ void __launch_bounds__(kBmThreads, 1) bm_mma_kernel(const __grid_cons
                 __syncwarp();   // the stage is reused by the next epilogue
             }
         }
+        if (warp == 0 && lane == 0) { BM_ACC_STORE(0, 27); BM_ACC_STORE(1, 28); BM_ACC_STORE(2, 29); }
     }
     tc_fence_before();
     __syncthreads();
@@ -1069,14 +1136,10 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
             rc = fill_src(src2, n_cols, 1, &one, b2, ld_full);
             if (rc != H2_OK) return rc;
         }
-        const size_t smem = (size_t)kChunkCols * (grid.y * dg + 1) * 4;
         const int S = splits_pieces(splits);
-#define H2_PACK_I8(DG_, S_)                                                                                                 \
-        do {                                                                                                                \
-            auto kern = bm_pack_i8_kernel<DG_, S_>;                                                                         \
-            H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-            kern<<<grid.x, 256, smem, st>>>(n_cols, d, (int)grid.y, src2, dinv_col, gmax4, blockmax, (int)L.n_blocks, xp);  \
-        } while (0)
+        const dim3 pgrid(grid.x, grid.y * (dg / kPackFeat));
+#define H2_PACK_I8(DG_, S_) \
+        bm_pack_i8_kernel<DG_, S_><<<pgrid, 128, 0, st>>>(n_cols, d, (int)grid.y, src2, dinv_col, gmax4, blockmax, (int)L.n_blocks, xp)
         if (dg == 32) { if (S == 2) H2_PACK_I8(32, 2); else H2_PACK_I8(32, 3); }
         else { if (S == 2) H2_PACK_I8(64, 2); else H2_PACK_I8(64, 3); }
 #undef H2_PACK_I8
@@ -1117,7 +1180,7 @@ static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cud
     constexpr size_t smem = BmCfg<DG, S, I8>::kSmem;
     auto kern = bm_mma_kernel<DG, S, I8>;
     H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<sc.n_ctas, kBmThreads, smem, st>>>(p);
+    kern<<<sc.n_ctas, bm_threads(I8), smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
     if (sc.n_fix > 0) {
         bm_fixup_kernel<DG><<<dim3((kTileRows * DG / 4 + 255) / 256, sc.n_fix), 256, 0, st>>>((const BmFix *)(base + sc.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
@@ -1175,5 +1238,9 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
 extern "C" int h2_debug_read(long long *host) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(host, h2::g_bm_trace, sizeof(long long) * 148 * 32);
+}
+extern "C" int h2_debug_read2(long long *host) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(host, h2::g_bm_trace2, sizeof(long long) * 8 * 64);
 }
 #endif

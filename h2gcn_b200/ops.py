@@ -179,7 +179,7 @@ class HopPlan:
     """
     MODES = {"auto": 0, "csr": 1, "tensor": 2}
 
-    def __init__(self, hops, factored=False, mode="auto", splits=2, stream=None):
+    def __init__(self, hops, factored=False, mode="auto", splits=None, stream=None):
         if not 1 <= len(hops) <= _cabi.MAX_HOPS:
             raise ValueError(f"between 1 and {_cabi.MAX_HOPS} hops per fused round, got {len(hops)}")
         if mode not in self.MODES:
@@ -334,7 +334,7 @@ class HostGraph:
     """h2_graph_*: adjacency resident on the device, X in / Y out through HOST buffers every call (bench.py e2e)."""
     MODES = {"auto": 0, "csr": 1, "tensor": 2}
 
-    def __init__(self, hops_host, n_rows, n_cols, d_max, dinv_host=None, row_begin=0, mode="auto", splits=2):
+    def __init__(self, hops_host, n_rows, n_cols, d_max, dinv_host=None, row_begin=0, mode="auto", splits=None):
         """hops_host: list of (rowptr int64, col int32, val fp32) numpy arrays; dinv_host: optional list of fp32
         [n_cols] scale vectors (normalised binary patterns) enabling the tensor-core format."""
         import numpy as np

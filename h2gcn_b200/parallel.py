@@ -92,7 +92,7 @@ class ShardedGraph:
     equal-rows split and all-gathered (they are also the global degree vector D2 the normalisation needs), the
     nnz-balanced boundaries are derived from them, then every rank fills and normalises its own rows."""
 
-    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=2, exchange="auto"):
+    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=None, exchange="auto"):
         from . import ops
         self.rank, self.world, self.device, self.group = rank, world, device, group
         a = adj_scipy.tocsr()

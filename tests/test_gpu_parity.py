@@ -298,7 +298,8 @@ def test_fused_program_is_used_and_counts_launches(dev):
     before = _cabi.launch_count()
     out = model(t.adj, t.features, t.adj_hops)
     plan = model.layer_objs[2].plan_for(t.adj_hops)
-    per_round = (1 if plan.csr_idx else 0) + 3 * len(plan.tensor_idx)      # gather | pack + mma + fix-up per bitmap hop
+    per_bm = 4 if plan.splits in (_cabi.H2_SPLITS_I8X2, _cabi.H2_SPLITS_I8X3) else 3
+    per_round = (1 if plan.csr_idx else 0) + per_bm * len(plan.tensor_idx)   # gather | [absmax +] pack + mma + fix-up per bitmap hop
     assert _cabi.launch_count() - before == 2 + 2 * per_round, "X.W0+relu, round 1, round 2, classifier"
     assert out.shape == (2708, 7)
     emb_model = H2GCN(parse_network_setup("M64-E-R-T1-G-V-C1-MO", 7))

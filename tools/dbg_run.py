@@ -13,8 +13,17 @@ splits = int(splits) if splits.isdigit() else splits
 g = ShardedGraph(adj, 0, 1, dev, splits=splits)
 x = torch.from_numpy(synth.features(10000, 128, 0)).to(dev); y = torch.empty(10000, 256, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+alone = len(sys.argv) > 2 and sys.argv[2] == "alone"     # only the tensor-core hop (no co-running CSR gather kernel)
+if alone:
+    from h2gcn_b200.ops import HopPlan
+    p2 = HopPlan([g.hops[1]], mode="tensor", splits=splits)
+    y1 = torch.empty(10000, 128, device=dev)
 for _ in range(3):
-    flush.zero_(); g.round(x, y, [0, 128])
+    flush.zero_()
+    if alone:
+        p2.run(x, y1, [0])
+    else:
+        g.round(x, y, [0, 128])
 torch.cuda.synchronize()
 lib = ctypes.CDLL(_cabi.SO_PATH)
 buf = np.zeros(148 * 32, dtype=np.int64)
@@ -35,3 +44,12 @@ for c in [0, 1, 2, 37, 73, 74, 100, 147]:
         if s[0] == 0: break
         segs.append([int(v - t0) for v in s])
     print(c, "end", int(r[1] - t0), segs)
+
+# per-unit timeline of CTA 0 (first 40 units): cycles relative to the CTA start
+b2 = np.zeros(8 * 64, dtype=np.int64)
+lib.h2_debug_read2(b2.ctypes.data_as(ctypes.c_void_p))
+b2 = b2.reshape(8, 64) - b[0, 0]
+names = ["TMA: stage free", "prod: B landed", "prod: expanded", "prod: A stage free", "prod: stored", "MMA: A ready", "MMA: issued"]
+print("unit " + " | ".join(n.rjust(18) for n in names))
+for u in range(40):
+    print("%4d " % u + " | ".join(("%18d" % b2[r, u]) if b2[r, u] > 0 else " " * 18 for r in range(7)))
