@@ -705,12 +705,12 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                 it += skip;
                 uint32_t ready = 0;
                 if (I8 && sg.unit_begin + skip < sg.unit_end) ready = mbar_try_wait(bar_full_b + 8 * (it % kBStages), (it / kBStages) & 1);
-                for (int u = sg.unit_begin + skip; u < sg.unit_end; u += kStep, it += kStep) {
+                // one unit: expand the bitmap row(s) into `a`, publish the previous unit, wait for a free A stage, store
+                auto produce = [&](int u, uint32_t (&a)[32]) {
                     const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
                     // the unit's bitmap rides in the B stage (TMA-prefetched)
                     if (!I8 || !ready) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(0); }
                     if ((warp & 3) == 0 && lane == 0) BM_T2(1, it);
-                    uint32_t a[32];
                     if constexpr (I8) {
                         // word j = columns 4j..4j+3 as bytes 0 / 2^t: the bits sit 8 apart (bm_bit_pos order 1), so a
                         // rotate brings them to bit t of each byte and a mask keeps them; {rotate, mask} per word ride
@@ -742,7 +742,6 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                         }
                     }
                     const uint32_t sa = it % kAStg, pa = (it / kAStg) & 1;
-                    if ((warp & 3) == 0 && lane == 0) BM_T2(2, it);
                     if (pending) {   // publish the previous unit BEFORE waiting for a free stage (it may be the same stage)
                         BM_WAIT_BEGIN();
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -758,6 +757,12 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                     if ((warp & 3) == 0 && lane == 0) BM_T2(4, it);
                     pending = true;
                     pending_sa = sa;
+                };
+                {
+                    // (measured dead end: two alternating register arrays, so that a tcgen05.st never has its source
+                    // registers overwritten by the next unit, change nothing)
+                    uint32_t a[32];
+                    for (int u = sg.unit_begin + skip; u < sg.unit_end; u += kStep, it += kStep) produce(u, a);
                 }
                 it = it_end;
                 if (pending) {
