@@ -28,6 +28,9 @@ L2_BYTES = 126 << 20
 DEFAULT_SPLITS = None      # arithmetic of the tensor-core path: None = the library default (h2gcn_b200._cabi.DEFAULT_SPLITS)
 
 
+_JSON_OUT = sys.stdout
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -153,7 +156,8 @@ def run_reference(args):
                              "sample": f"{args.steps} full fused rounds; C restatement of tf.sparse.sparse_dense_matmul "
                                        "(TF-CPU functor order) with OpenMP over rows — TensorFlow itself is absent"},
             "e2e": {"value": val, "unit": "edges*featdim/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
@@ -171,6 +175,12 @@ def main():
     ap.add_argument("--splits", default=DEFAULT_SPLITS, help="arithmetic of the tensor-core path: 2 | 3 (bf16 pieces), i8x2 | i8x3 "
                     "(int8 digits with per-4-row block exponents, exact int32 accumulation)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: anything a library writes to fd 1 (NCCL prints its version banner there
+    # when NCCL_DEBUG is set) is sent to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     from h2gcn_b200 import _cabi as _c
     args.splits = _c.splits_code(args.splits)
     if args.impl == "reference":
@@ -384,7 +394,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(g.hops_host(), x_full, y_gpu=y.cpu().numpy())
         line["config"]["parity"] = line["cpu_baseline"].pop("parity_of_timed_path")
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
