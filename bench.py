@@ -285,6 +285,39 @@ def main():
         b.record()
     torch.cuda.synchronize()
     times = np.array([a.elapsed_time(b) for a, b in ev])  # ms
+
+    # secondary figures: the same round with the other arithmetics of the tensor-core path (same replicas-larger-than-L2
+    # scheme, fewer steps).  Never allowed to break the headline line.
+    other = {}
+    if world == 1 and args.mode == "auto":
+        for name in ("i8x2", "i8x3", "bf16x2"):
+            code = _cabi.splits_code(name)
+            if code == args.splits:
+                continue
+            try:
+                alt = [ShardedGraph(adj, rank, world, dev, factored=args.factored, mode=args.mode, splits=code,
+                                    exchange=args.exchange) for _ in range(R)]
+                ya = torch.empty(g.n_local, 2 * d, device=dev)
+
+                def alt_step(k):
+                    with torch.cuda.stream(lanes[k % len(lanes)]):
+                        alt[k % R].round(xs[k % R], ys[k % R] if k % R else ya, [0, d])
+                for k in range(max(args.warmup, R)):
+                    alt_step(k)
+                torch.cuda.synchronize()
+                k_alt = min(args.steps, 300)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                fork()
+                for k in range(k_alt):
+                    alt_step(k)
+                join()
+                eb.record()
+                torch.cuda.synchronize()
+                other[_cabi.SPLITS_NAME[code]] = {"ms_per_step": float(ea.elapsed_time(eb)) / k_alt, "steps": k_alt}
+                del alt
+            except Exception as exc:  # noqa: BLE001
+                other[name] = {"error": repr(exc)[:200]}
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -379,7 +412,8 @@ def main():
                    "ms_per_step_l2_flush_events": float(times.mean()), "ms_per_step_l2_flush_events_min": float(times.min()),
                    "l2_flush_note": f"secondary: {k_fl} steps, each after a {L2_FLUSH_BYTES >> 20} MiB L2-flush write and "
                                     "bracketed by its own event pair (includes ~4 us of event overhead per step)",
-                   "precompute_s": t_pre, "wall_s_timed_region": wall},
+                   "precompute_s": t_pre, "wall_s_timed_region": wall,
+                   "arithmetic": _cabi.SPLITS_NAME[args.splits], "other_arithmetics": other},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": balg,
                      "kernel_ms": kern_ms, "note": "compulsory bytes of one round (SURVEY §8d, explicit fp32 values, "
