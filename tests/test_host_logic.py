@@ -68,3 +68,61 @@ def test_glorot_uniform_bounds():
     w = L.glorot_uniform(100, 50, "cpu", torch.Generator().manual_seed(0))
     lim = (6.0 / 150) ** 0.5
     assert w.shape == (100, 50) and float(w.abs().max()) <= lim and float(w.std()) > 0.3 * lim
+
+
+# ---- arithmetic codes of the tensor-core path and the numpy model of its int8 operand (no kernel is launched) -----------
+def test_splits_codes():
+    from h2gcn_b200 import _cabi
+    assert _cabi.splits_code(2) == 2 and _cabi.splits_code("3") == 3 and _cabi.splits_code("bf16x2") == 2
+    assert _cabi.splits_code("i8x2") == _cabi.H2_SPLITS_I8X2 == 18 and _cabi.splits_code(19) == _cabi.H2_SPLITS_I8X3
+    assert _cabi.splits_code(None) == _cabi.splits_code(_cabi.DEFAULT_SPLITS)
+    assert set(_cabi.SPLITS_NAME) == {2, 3, 18, 19}
+    for bad in (4, "i8x4", "fp8", 1.5):
+        with pytest.raises(ValueError):
+            _cabi.splits_code(bad)
+
+
+@pytest.mark.parametrize("pieces,rng_bound", [(2, 32639), (3, 8355711)])
+def test_int8_operand_model(pieces, rng_bound):
+    """tests/util.py: i8_block_quantize is the model the GPU test compares the int8 kernel with EXACTLY: its own
+    invariants — digits range, block exponents 0..6 relative to the global maximum, error bound per element."""
+    from tests import util
+    rng = np.random.default_rng(pieces)
+    x = (rng.standard_normal((403, 24)) * np.exp(rng.uniform(-12, 0, size=(403, 1)))).astype(np.float32)
+    x[100:104] = 0.0
+    deq, step, t = util.i8_block_quantize(x, pieces)
+    assert t.min() >= 0 and t.max() <= 6 and len(t) == 101 and t[25] == 0           # 403 rows -> 101 groups of 4
+    g = int(np.argmax(np.abs(x).max(axis=1))) // 4
+    assert t[g] == 6, "the group holding the global maximum gets the largest block exponent"
+    q = deq / (step * np.ldexp(1.0, np.repeat(t, 4)[:403])[:, None])
+    assert np.allclose(q, np.rint(q)) and np.abs(q).max() <= rng_bound
+    # |error| <= half a step of the element's group (+ the fp32 rounding of the scaled value)
+    bound = 0.5 * step * np.ldexp(1.0, np.repeat(t, 4)[:403])[:, None] * (1 + 1e-6) + np.abs(x) * 2.0 ** -23
+    assert (np.abs(deq - x) <= bound).all()
+    # balanced base-256 digits reproduce q
+    qi = np.rint(q).astype(np.int64)
+    rest, digits = qi.copy(), []
+    for _ in range(pieces):
+        dgt = ((rest + 128) & 255) - 128
+        digits.append(dgt)
+        rest = (rest - dgt) >> 8
+    assert (rest == 0).all() and all((dg >= -128).all() and (dg <= 127).all() for dg in digits)
+    assert (sum(dg * 256 ** k for k, dg in enumerate(digits)) == qi).all()
+    assert (util.i8_block_quantize(np.zeros((8, 4), np.float32), pieces)[0] == 0).all()
+
+
+def test_bitmap_bit_order_is_a_permutation():
+    """bm_bit_pos order 1 (csrc/bitmap_mma.cu): bit(c) = 32*(c/32) + 8*(c%4) + (c%32)/4 — the four columns of operand word
+    j = c/4 land 8 bits apart at bit (j % 8) of each byte, so word j = rotate(x, j%8 - t) & (0x01010101 << t)."""
+    pos = [32 * (c // 32) + 8 * (c % 4) + (c % 32) // 4 for c in range(64)]
+    assert sorted(pos) == list(range(64))
+    for c in range(64):
+        j, k = c // 4, c % 4
+        assert pos[c] // 32 == j // 8 and pos[c] % 32 == 8 * k + j % 8
+    for t in range(7):                                   # the expansion identity, on every single-bit row
+        for c in range(64):
+            x = (1 << pos[c]) >> (32 * (c // 32)) & 0xFFFFFFFF
+            j = c // 4
+            r = ((j % 8) - t) & 31
+            word = ((x >> r) | (x << (32 - r))) & 0xFFFFFFFF & ((0x01010101 << t) & 0xFFFFFFFF)
+            assert word == (1 << t) << (8 * (c % 4)), (t, c)
