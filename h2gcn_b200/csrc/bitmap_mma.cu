@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -53,7 +54,7 @@ constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in sh
 #endif
 __host__ __device__ constexpr int bm_producer_sets(bool i8) { return i8 ? H2_BM_I8_SETS : 1; }
 __host__ __device__ constexpr int bm_threads(bool i8) { return (8 * bm_producer_sets(i8) + 2) * 32; }   // producers, TMA warp, MMA warp (last)
-constexpr uint32_t kBmMagic = 0x48324233u;  // "H2B3"
+constexpr uint32_t kBmMagic = 0x48324234u;  // "H2B4"
 constexpr int kAStagesMax = 8;   // int8 A tiles are half as wide: up to 8 stages of 32 TMEM columns
 
 // `splits` codes (include/h2gcn_b200.h): 2 / 3 = bf16 pieces; H2_SPLITS_I8X2 / H2_SPLITS_I8X3 = int8 digits with
@@ -92,6 +93,7 @@ struct BmFix {           // one (row tile, column group) whose result is the ord
 };
 
 constexpr int kNumScheds = 4;   // stream-K schedules for 1, 2, 4, 8 column groups (work items are group-major)
+constexpr int kNumPairScheds = 3;
 struct BmSched {
     int32_t n_ctas, n_partial_slots, n_fix, pad;
     int64_t off_seg, off_cta_seg_ptr, off_fix;
@@ -106,6 +108,7 @@ struct BmHost {          // host header (caller's bm_host buffer)
     // offsets (bytes) into the device plan buffer
     int64_t off_unit_chunk, off_bits, off_empty_tiles, n_empty_tiles;
     BmSched sched[kNumScheds];
+    BmSched sched_pair[kNumPairScheds];   // CTA-pair kernel: <= 74 pairs, 1 / 2 / 4 column groups of 128 features
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -847,6 +850,286 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair form of the int8 kernel (i8x2, d > 64): `tcgen05.mma.cta_group::2`, M = 256 = 128 rows per CTA, N = 256 = all
+// 2 digits x 128 features of a 128-feature column group.  CTA r of the pair owns rows [128 r, 128 r + 128) of a 256-row
+// tile: it loads ITS half of the unit's bitmap (1 KB) and ITS half of the B tile — the [128 x 64] tile of the 64-feature
+// group 2 pg + r, so the packed operand is the one the single-CTA kernel uses — and expands every bitmap row ONCE (the
+// single-CTA kernel visits a unit once per 64-feature group: twice).  The leader (rank 0) issues the MMAs for both CTAs;
+// its "A ready" barrier collects the producer warps of both CTAs (remote `mbarrier.arrive` through `mapa`), the "stage
+// free" / "accumulator full" commits are multicast to both CTAs, its "accumulator drained" barrier collects both
+// epilogues.  Verified in isolation by tools/umma_pair_probe.cu (bit-exact, 128 cycles per M256 N256 K32).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPairAStages = 16;       // 16 TMEM columns each (128 rows x 64 int8), after the 256 accumulator columns
+constexpr int kPairThreads = 320;      // 8 producer / epilogue warps, TMA warp, MMA warp
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals come from the peer CTA too
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+struct BmPairCfg {
+    static constexpr int S = 2, DG = 64, NBH = S * DG;                    // this CTA's half of the B tile: [128 x 64] int8
+    static constexpr uint32_t kBBytes = NBH * 64 + kI8ConstBytes;
+    static constexpr uint32_t kBStride = (kBBytes + 1023u) & ~1023u;
+    static constexpr uint32_t kBitsBytes = 128 * 8;                       // this CTA's 128 bitmap rows of a unit
+    static constexpr size_t kSmem = (size_t)kBStages * (kBStride + kBitsBytes) + 8 * 32 * (DG + 4) * 4 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_mma_pair_kernel(const __grid_constant__ BmParams p) {
+    using Cfg = BmPairCfg;
+    constexpr int S = Cfg::S, DG = Cfg::DG, NBH = Cfg::NBH;
+    constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride, kBitsBytes = Cfg::kBitsBytes;
+    constexpr uint32_t kACol0 = 256, kTmemCols = 512;
+    constexpr int kAStg = kPairAStages;
+    // D int32 | A, B signed int8 | N = 256 | M = 256 (128 rows per CTA)
+    constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t smem_raw_u32 = smem_u32(smem_raw);
+    asm volatile("" : "+r"(smem_raw_u32));
+    const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+    const uint32_t bits_base = smem_base + kBStages * kBStride;
+    const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_raw_u32));
+    constexpr int kStageStride = DG + 4;
+    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kBStages * kBitsBytes);
+    __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStages + 2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_chunk[32];
+    uint32_t bar0 = smem_u32(&s_bar[0]);
+    asm volatile("" : "+r"(bar0));
+    const uint32_t bar_full_a = bar0;                                   // leader only: 8 producer warps (4 of each CTA)
+    const uint32_t bar_empty_a = bar0 + 8 * kAStg;                      // multicast commit
+    const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);                 // local TMA
+    const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kBStages);     // multicast commit
+    const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kBStages);       // multicast commit
+    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kBStages + 1);  // leader only: 16 epilogue warps
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int seg_begin = p.cta_seg_ptr[pair], seg_end = p.cta_seg_ptr[pair + 1];
+    const int n_work = seg_end - seg_begin;
+    constexpr int kTmaWarp = 8, kMmaWarp = 9;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kAStg; ++s) {
+            mbar_init(bar_full_a + 8 * s, 8);
+            mbar_init(bar_empty_a + 8 * s, 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(bar_full_b + 8 * s, 1);
+            mbar_init(bar_empty_b + 8 * s, 1);
+        }
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_empty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {   // the same warp of both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == kTmaWarp) {
+        // ===== TMA producer: this CTA's half of the B tile (+ constants) and of the unit's bitmap =====
+        uint32_t it = 0;
+        for (int w = 0; w < n_work; ++w) {
+            const BmSegment sg = p.seg[seg_begin + w];
+            const int g = 2 * sg.group + (int)rank;        // 64-feature group whose [128 x 64] tile is this CTA's half
+            int nxt = sg.unit_begin + lane < sg.unit_end ? p.unit_chunk[sg.unit_begin + lane] : 0;
+            for (int u0 = sg.unit_begin; u0 < sg.unit_end; u0 += 32) {
+                s_chunk[lane] = nxt;
+                __syncwarp();
+                if (u0 + 32 + lane < sg.unit_end) nxt = p.unit_chunk[u0 + 32 + lane];
+                const int cnt = min(32, sg.unit_end - u0);
+                if (elect_one()) {
+                    for (int k = 0; k < cnt; ++k) {
+                        const int chunk = s_chunk[k];
+                        const uint32_t st = (it + k) % kBStages, ph = ((it + k) / kBStages) & 1;
+                        mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
+                        mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kBitsBytes);
+                        const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
+                        bulk_copy_g2s(smem_base + st * kBStride, src, kBBytes, bar_full_b + 8 * st);
+                        bulk_copy_g2s(bits_base + st * kBitsBytes, p.bits + (int64_t)(u0 + k) * kTileRows + rank * 128, kBitsBytes,
+                                      bar_full_b + 8 * st);
+                    }
+                }
+                it += cnt;
+                __syncwarp();
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer: the leader's elected lane, for both CTAs =====
+        if (rank == 0 && elect_one()) {
+            uint32_t it = 0, acc_it = 0;
+            for (int w = 0; w < n_work; ++w) {
+                const BmSegment sg = p.seg[seg_begin + w];
+                mbar_wait_cluster(bar_acc_empty, (acc_it & 1) ^ 1);   // both epilogues have drained the accumulators
+                tc_fence_after();
+                uint32_t acc = 0;
+                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
+                    const uint32_t sa = it % kAStg, sb = it % kBStages;
+                    mbar_wait_cluster(bar_full_a + 8 * sa, (it / kAStg) & 1);   // both CTAs: A stored (and B landed)
+                    tc_fence_after();
+                    const uint32_t b0 = smem_base + sb * kBStride;
+                    const uint32_t a0 = tmem_base + kACol0 + sa * 16;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_i8_ts_pair(tmem_base, a0 + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc, k > 0 ? 1u : acc);
+                    acc = 1;
+                    umma_commit_pair(bar_empty_a + 8 * sa);
+                    umma_commit_pair(bar_empty_b + 8 * sb);
+                }
+                umma_commit_pair(bar_acc_full);
+                ++acc_it;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== A producers (4-warp groups on alternate units, one bitmap row per thread), then epilogue =====
+        const int grp = warp >> 2, quarter = warp & 3;
+        const int r = quarter * 32 + lane;                       // row inside this CTA's 128-row half
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t full_a_leader = mapa_u32(bar_full_a, 0), acc_empty_leader = mapa_u32(bar_acc_empty, 0);
+        uint32_t it = 0, acc_it = 0;
+        for (int w = 0; w < n_work; ++w, ++acc_it) {
+            const BmSegment sg = p.seg[seg_begin + w];
+            bool pending = false;
+            uint32_t pending_sa = 0;
+            const int skip = (int)((uint32_t)(grp + 2 - (int)(it % 2)) % 2);
+            const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
+            it += skip;
+            for (int u = sg.unit_begin + skip; u < sg.unit_end; u += 2, it += 2) {
+                const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
+                mbar_wait(bar_full_b + 8 * sb, pb);
+                const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
+                const unsigned long long b0 = bits_gen[sb * 128 + r];
+                const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32);
+                uint32_t a[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 c = cst[q];
+                    const uint32_t x = q < 4 ? x0 : x1;
+                    a[2 * q] = __funnelshift_r(x, x, c.x) & c.y;
+                    a[2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
+                }
+                const uint32_t sa = it % kAStg, pa = (it / kAStg) & 1;
+                if (pending) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * pending_sa);
+                }
+                mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
+                tc_fence_after();
+                cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 16, a);
+                pending = true;
+                pending_sa = sa;
+            }
+            it = it_end;
+            if (pending) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * pending_sa);
+            }
+            // ---- epilogue: warp = (lane quarter, 64-feature sub-group = which half of the 256 accumulator columns) ----
+            mbar_wait(bar_acc_full, acc_it & 1);
+            tc_fence_after();
+            const int sub = grp;                                   // columns [128 sub, 128 sub + 128): digits of group 2 pg + sub
+            const int g = 2 * sg.group + sub;
+            const int64_t grow = (int64_t)sg.tile * kTileRows + rank * 128 + r;
+            const bool row_ok = grow < p.n_rows;
+            const float scale = __ldg(p.xstep) * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
+            const int valid_cols = sg.partial_slot < 0 ? max(0, min(DG, p.d - g * DG)) : DG;
+            float *stage = stage_gen + warp * (32 * kStageStride);
+#pragma unroll 1
+            for (int c0 = 0; c0 < DG; c0 += 32) {
+                uint32_t acc[S][32];
+#pragma unroll
+                for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_lane + sub * NBH + s * DG + c0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float4 o;
+                    float *po = &o.x;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)   // digits, most significant first
+                        po[e] = fmaf((float)(int32_t)acc[0][q + e], 256.f, (float)(int32_t)acc[1][q + e]) * scale;
+                    *reinterpret_cast<float4 *>(stage + lane * kStageStride + c0 + q) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader);   // drained: the next segment's MMAs may start
+            {
+                constexpr int kLanesPerRow = DG / 4, kRowsPerInstr = 32 / kLanesPerRow;
+                const int rr = lane / kLanesPerRow, c = (lane % kLanesPerRow) * 4;
+                const int row0 = (int)rank * 128 + quarter * 32;
+                const bool col_ok = c + 4 <= valid_cols;
+#pragma unroll
+                for (int j = 0; j < 32; j += kRowsPerInstr) {
+                    const int row = j + rr;
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + c);
+                    const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
+                    float *drow = sg.partial_slot < 0 ? p.Y + gr * p.ldy + (int64_t)g * DG
+                                                       : p.partial + ((int64_t)sg.partial_slot * kTileRows + row0 + row) * (2 * DG) + sub * DG;
+                    if (col_ok && (sg.partial_slot >= 0 || gr < p.n_rows)) *reinterpret_cast<float4 *>(drow + c) = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // no CTA frees tensor memory or exits while its peer can still signal it
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // fix-up: Y[tile rows, group columns] = sum over the partial slots of that (tile, group), ascending slot order
 // (deterministic).  One thread per output float4; grid = (256 * DG/4 / 256, n_fix).
 template <int DG>
@@ -957,6 +1240,7 @@ extern "C" size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n
     size_t b = align_up_sz((size_t)n_units * 4, 256) + align_up_sz((size_t)n_units * kTileRows * 8, 256) +
                align_up_sz((size_t)(nt + 1) * 4, 256) + 1024;
     for (int k = 0; k < kNumScheds; ++k) b += sched_bytes(nt, 1 << k);
+    for (int k = 0; k < kNumPairScheds; ++k) b += sched_bytes(nt, 1 << k);
     return b;
 }
 
@@ -1010,14 +1294,15 @@ extern "C" int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *r
         if (tp[q + 1] == tp[q]) empty_tiles.push_back((int32_t)q);
     h->n_empty_tiles = (int64_t)empty_tiles.size();
     if (!empty_tiles.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_empty_tiles, empty_tiles.data(), empty_tiles.size() * 4, cudaMemcpyHostToDevice, st));
-    std::vector<BmSegment> segs[kNumScheds];
-    std::vector<int32_t> cta_ptr[kNumScheds];
-    std::vector<BmFix> fixes[kNumScheds];
-    for (int k = 0; k < kNumScheds; ++k) {
-        const int ng = 1 << k;
+    std::vector<BmSegment> segs[kNumScheds + kNumPairScheds];
+    std::vector<int32_t> cta_ptr[kNumScheds + kNumPairScheds];
+    std::vector<BmFix> fixes[kNumScheds + kNumPairScheds];
+    for (int k = 0; k < kNumScheds + kNumPairScheds; ++k) {
+        const bool pair = k >= kNumScheds;       // schedules of the CTA-pair kernel: one range per PAIR of CTAs
+        const int ng = 1 << (pair ? k - kNumScheds : k);
         const int64_t total = n_units * ng;
-        const int G = (int)std::min<int64_t>(kNumSms, total);
-        BmSched &sc = h->sched[k];
+        const int G = (int)std::min<int64_t>(pair ? kNumSms / 2 : kNumSms, total);
+        BmSched &sc = pair ? h->sched_pair[k - kNumScheds] : h->sched[k];
         cta_ptr[k].assign(G + 1, 0);
         int n_slots = 0;
         // Every (group, tile) item a CTA enters costs an epilogue (TMEM drain + write-out + pipeline refill, measured
@@ -1086,13 +1371,25 @@ extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
     return (size_t)(nc * ng * splits * dg * 128) + 256;
 }
 
+// The CTA-pair kernel covers 2 int8 digits and an even number of 64-feature groups (d > 64).  OPT-IN (H2_BM_PAIR=1):
+// bit-identical results and the same round time as the single-CTA kernel on the box (47.7 vs 47.1-48.9 us, profiles/
+// README.md r01f) although every bitmap row is expanded once instead of twice — so the producers' ALU work is not what
+// bounds either kernel; kept as the starting point for the next round.
+static bool pair_kernel_applies(int32_t splits, int n_groups64) {
+    static const bool enabled = [] { const char *e = getenv("H2_BM_PAIR"); return e && e[0] == '1'; }();
+    return enabled && splits == H2_SPLITS_I8X2 && n_groups64 >= 2 && n_groups64 <= 8 && n_groups64 % 2 == 0;
+}
+
 extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits) {
     const BmHost *h = (const BmHost *)bm_host;
     if (!h || h->magic != kBmMagic || !splits_valid(splits)) return 0;
     const int dg = dg_for(d, splits);
     const int ng = groups_for(d, dg);
     if (ng > 8) return 0;
-    return (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4 + 256;
+    size_t b = (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4;
+    if (dg == 64 && ng >= 2)   // either kernel may run (the switch is read per call)
+        b = std::max(b, (size_t)h->sched_pair[sched_index(ng / 2)].n_partial_slots * kTileRows * 128 * 4);
+    return b + 256;
 }
 
 namespace h2 {
@@ -1233,6 +1530,21 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
         H2_LAUNCHED("bm_zero_tiles_kernel");
     }
     if (sc.n_ctas == 0) return H2_OK;
+    if (dg == 64 && pair_kernel_applies(splits, n_groups)) {
+        const BmSched &sp = h->sched_pair[sched_index(n_groups / 2)];
+        H2_REQUIRE(sp.n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits)), H2_ERR_WORKSPACE,
+                   "h2_bm_spmm_f32: partial workspace too small");
+        p.seg = (const BmSegment *)(base + sp.off_seg);
+        p.cta_seg_ptr = (const int32_t *)(base + sp.off_cta_seg_ptr);
+        H2_CUDA(cudaFuncSetAttribute(bm_mma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BmPairCfg::kSmem));
+        bm_mma_pair_kernel<<<2 * sp.n_ctas, kPairThreads, BmPairCfg::kSmem, st>>>(p);   // __cluster_dims__(2, 1, 1)
+        H2_LAUNCHED("bm_mma_pair_kernel");
+        if (sp.n_fix > 0) {
+            bm_fixup_kernel<128><<<dim3((kTileRows * 128 / 4 + 255) / 256, sp.n_fix), 256, 0, st>>>((const BmFix *)(base + sp.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
+            H2_LAUNCHED("bm_fixup_kernel");
+        }
+        return H2_OK;
+    }
     if (splits == H2_SPLITS_I8X2) return dg == 32 ? bm_launch<32, 2, true>(sc, base, p, st) : bm_launch<64, 2, true>(sc, base, p, st);
     if (splits == H2_SPLITS_I8X3) return dg == 32 ? bm_launch<32, 3, true>(sc, base, p, st) : bm_launch<64, 3, true>(sc, base, p, st);
     if (splits == 2) return dg == 32 ? bm_launch<32, 2>(sc, base, p, st) : bm_launch<64, 2>(sc, base, p, st);
