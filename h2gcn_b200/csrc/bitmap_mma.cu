@@ -862,6 +862,10 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPairAStages = 16;       // 16 TMEM columns each (128 rows x 64 int8), after the 256 accumulator columns
 constexpr int kPairThreads = 320;      // 8 producer / epilogue warps, TMA warp, MMA warp
+#ifndef H2_BM_PAIR_B_STAGES
+#define H2_BM_PAIR_B_STAGES 8
+#endif
+constexpr int kPairBStages = H2_BM_PAIR_B_STAGES;   // B half tiles (9 KB) + bitmap halves (1 KB); up to 14 fit next to the epilogue stage
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -908,7 +912,7 @@ struct BmPairCfg {
     static constexpr uint32_t kBBytes = NBH * 64 + kI8ConstBytes;
     static constexpr uint32_t kBStride = (kBBytes + 1023u) & ~1023u;
     static constexpr uint32_t kBitsBytes = 128 * 8;                       // this CTA's 128 bitmap rows of a unit
-    static constexpr size_t kSmem = (size_t)kBStages * (kBStride + kBitsBytes) + 8 * 32 * (DG + 4) * 4 + 1024;
+    static constexpr size_t kSmem = (size_t)kPairBStages * (kBStride + kBitsBytes) + 8 * 32 * (DG + 4) * 4 + 1024;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_mma_pair_kernel(const __grid_constant__ BmParams p) {
@@ -924,11 +928,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
     uint32_t smem_raw_u32 = smem_u32(smem_raw);
     asm volatile("" : "+r"(smem_raw_u32));
     const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-    const uint32_t bits_base = smem_base + kBStages * kBStride;
+    const uint32_t bits_base = smem_base + kPairBStages * kBStride;
     const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_raw_u32));
     constexpr int kStageStride = DG + 4;
-    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kBStages * kBitsBytes);
-    __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStages + 2];
+    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kPairBStages * kBitsBytes);
+    __shared__ uint64_t s_bar[2 * kAStg + 2 * kPairBStages + 2];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_chunk[32];
     uint32_t bar0 = smem_u32(&s_bar[0]);
@@ -936,9 +940,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
     const uint32_t bar_full_a = bar0;                                   // leader only: 8 producer warps (4 of each CTA)
     const uint32_t bar_empty_a = bar0 + 8 * kAStg;                      // multicast commit
     const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);                 // local TMA
-    const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kBStages);     // multicast commit
-    const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kBStages);       // multicast commit
-    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kBStages + 1);  // leader only: 16 epilogue warps
+    const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kPairBStages);     // multicast commit
+    const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kPairBStages);       // multicast commit
+    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kPairBStages + 1);  // leader only: 16 epilogue warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -952,7 +956,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
             mbar_init(bar_full_a + 8 * s, 8);
             mbar_init(bar_empty_a + 8 * s, 1);
         }
-        for (int s = 0; s < kBStages; ++s) {
+        for (int s = 0; s < kPairBStages; ++s) {
             mbar_init(bar_full_b + 8 * s, 1);
             mbar_init(bar_empty_b + 8 * s, 1);
         }
@@ -986,7 +990,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
                 if (elect_one()) {
                     for (int k = 0; k < cnt; ++k) {
                         const int chunk = s_chunk[k];
-                        const uint32_t st = (it + k) % kBStages, ph = ((it + k) / kBStages) & 1;
+                        const uint32_t st = (it + k) % kPairBStages, ph = ((it + k) / kPairBStages) & 1;
                         mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
                         mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kBitsBytes);
                         const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
@@ -1009,7 +1013,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
                 tc_fence_after();
                 uint32_t acc = 0;
                 for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    const uint32_t sa = it % kAStg, sb = it % kBStages;
+                    const uint32_t sa = it % kAStg, sb = it % kPairBStages;
                     mbar_wait_cluster(bar_full_a + 8 * sa, (it / kAStg) & 1);   // both CTAs: A stored (and B landed)
                     tc_fence_after();
                     const uint32_t b0 = smem_base + sb * kBStride;
@@ -1041,7 +1045,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
             const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
             it += skip;
             for (int u = sg.unit_begin + skip; u < sg.unit_end; u += 2, it += 2) {
-                const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
+                const uint32_t sb = it % kPairBStages, pb = (it / kPairBStages) & 1;
                 mbar_wait(bar_full_b + 8 * sb, pb);
                 const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
                 const unsigned long long b0 = bits_gen[sb * 128 + r];
