@@ -1,7 +1,9 @@
 // Probe for the int8 tensor-core path (tcgen05.mma kind::i8, A from TENSOR MEMORY, B from shared memory):
 //   1. correctness of one M128 x N x K64 product for several shared-memory layouts of the K-major int8 B tile
 //      (no swizzle / SWIZZLE_64B / SWIZZLE_128B with half-used rows) against a CPU product;
-//   2. cycles per instruction of kind::i8 (K=32) next to kind::f16 (K=16), one CTA per SM, one elected issuer.
+//   2. cycles per instruction of kind::i8 (K=32) next to kind::f16 (K=16), one CTA per SM, one elected issuer;
+//   3. completion latency of tcgen05.st (x16 / x32) with and without a stream of MMAs in flight (not yet run: added at
+//      the end of round 1 to test whether the TMEM store latency is what paces the A producers).
 // Build + run on the GPU box:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/umma_i8_probe tools/umma_i8_probe.cu && /tmp/umma_i8_probe
 #include <cuda_runtime.h>
@@ -230,6 +232,97 @@ static void rate(const char *name) {
     cudaFree(out);
 }
 
+// ---- tcgen05.st completion latency, with and without a stream of MMAs in flight ------------------------------------------
+// Warps 1..3 store 16 (or 32) columns into their TMEM lanes and time `tcgen05.st` -> `tcgen05.wait::st`; warp 0's elected
+// lane keeps the tensor pipe busy with kind::i8 MMAs (A from TMEM, B from shared memory) when `with_mma` is set.  The A
+// producers of bm_mma_kernel wait for exactly this latency once per unit (deferred by one unit).
+template <int COLS>
+__global__ void __launch_bounds__(128, 1) sttm_latency_kernel(int iters, int with_mma, long long *out /*[grid][3]*/) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int done_warps;   // the timing warps count themselves out; the MMA lane stops when all three are done
+    const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        done_warps = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 16384 / 16; i += 128) reinterpret_cast<uint4 *>(smem + (base - smem_u32(smem)))[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_base_s;
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    if (warp == 0) {
+        if (with_mma && elect_one()) {
+            while (*(volatile int *)&done_warps < 3) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)   // A at columns 256.., accumulators 0..255: disjoint from the stores at 384..
+                    mma_i8_ts(tm + (k & 1) * 128, tm + 256 + (k & 1) * 8, make_desc(base + (k & 1) * 32, 0, 512, 4), idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            mbar_wait(smem_u32(&bar), 0);
+        }
+        __syncwarp();
+    } else {
+        uint32_t v[32];
+        for (int i = 0; i < 32; ++i) v[i] = i * 0x01010101u + lane;
+        const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + 384;
+        long long sum = 0, mx = 0;
+        for (int i = 0; i < iters; ++i) {
+            const long long t0 = clock64();
+            if (COLS == 16)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                             :: "r"(taddr), "r"(v[0]),"r"(v[1]),"r"(v[2]),"r"(v[3]),"r"(v[4]),"r"(v[5]),"r"(v[6]),"r"(v[7]),
+                                "r"(v[8]),"r"(v[9]),"r"(v[10]),"r"(v[11]),"r"(v[12]),"r"(v[13]),"r"(v[14]),"r"(v[15]) : "memory");
+            else
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                             :: "r"(taddr), "r"(v[0]),"r"(v[1]),"r"(v[2]),"r"(v[3]),"r"(v[4]),"r"(v[5]),"r"(v[6]),"r"(v[7]),"r"(v[8]),"r"(v[9]),"r"(v[10]),"r"(v[11]),"r"(v[12]),"r"(v[13]),"r"(v[14]),"r"(v[15]),
+                                "r"(v[16]),"r"(v[17]),"r"(v[18]),"r"(v[19]),"r"(v[20]),"r"(v[21]),"r"(v[22]),"r"(v[23]),"r"(v[24]),"r"(v[25]),"r"(v[26]),"r"(v[27]),"r"(v[28]),"r"(v[29]),"r"(v[30]),"r"(v[31]) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            const long long dt = clock64() - t0;
+            sum += dt;
+            mx = dt > mx ? dt : mx;
+            for (volatile int d = 0; d < 16; ++d) {}
+        }
+        if (lane == 0) {
+            out[(blockIdx.x * 3 + (warp - 1)) * 2] = sum / iters;
+            out[(blockIdx.x * 3 + (warp - 1)) * 2 + 1] = mx;
+            atomicAdd(&done_warps, 1);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+    }
+}
+
+template <int COLS>
+static void sttm_latency(int with_mma) {
+    const int grid = 148, iters = 2000, smem = 16384 + 2048;
+    long long *out;
+    cudaMalloc(&out, sizeof(long long) * grid * 6);
+    cudaFuncSetAttribute(sttm_latency_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    sttm_latency_kernel<COLS><<<grid, 128, smem>>>(iters, with_mma, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    static long long h[148 * 6];
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0; long long mx = 0;
+    for (int i = 0; i < grid * 3; ++i) { avg += (double)h[2 * i]; mx = h[2 * i + 1] > mx ? h[2 * i + 1] : mx; }
+    printf("tcgen05.st x%d -> wait::st: avg %.0f cycles, max %lld, %s MMAs in flight (%s)\n", COLS, avg / (grid * 3), mx,
+           with_mma ? "with" : "without", cudaGetErrorString(e));
+    cudaFree(out);
+}
+
 int main() {
     for (int layout = 0; layout < 3; ++layout) {
         check<128>(layout, 1);
@@ -246,5 +339,7 @@ int main() {
     rate<192, true, 1>("i8  TS N=192 K=32 (sw64)");
     rate<256, true, 1>("i8  TS N=256 K=32 (sw64)");
     rate<256, false, 2>("f16 TS N=256 K=16 (sw128)");
+    sttm_latency<16>(0); sttm_latency<16>(1);
+    sttm_latency<32>(0); sttm_latency<32>(1);
     return 0;
 }
