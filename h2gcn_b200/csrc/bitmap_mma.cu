@@ -28,6 +28,16 @@
 // Work items are (column group, unit) pairs, group-major, cut into <= 148 equal contiguous ranges (stream-K); a range
 // that does not cover a whole (row tile, group) writes an fp32 partial tile and `bm_fixup_kernel` adds the partials
 // of a tile in ascending slot order (deterministic).  Measurements behind these choices: profiles/README.md.
+//
+// Arithmetics (`splits`, include/h2gcn_b200.h).  The description above is the bf16 one (kind::f16, 2 / 3 pieces of X').
+// The DEFAULT is int8 (`I8 = true`, H2_SPLITS_I8X2 / I8X3): X' as block-fixed-point — one step for the matrix, a block
+// exponent 2^t (t in 0..6) per 4 rows carried by the 0/1 operand as bytes 0 / 2^t, 2 / 3 balanced base-256 digits as
+// the int8 B operand — on `tcgen05.mma kind::i8` (K = 32, twice the bf16 MAC rate, EXACT int32 accumulation; the
+// epilogue converts and scales once).  Differences: bm_absmax_kernel + bm_pack_i8_kernel build the operand (B tiles of
+// [S*DG x 64] bytes, SWIZZLE_64B, + 128 bytes of per-word {rotate, mask} constants); bitmaps in bit order 1 so that
+// an operand word is one rotate + one mask; A stages of 2 x 16 TMEM columns (8 of them); the 8 producer warps form
+// two groups of 4 that take alternate units and expand two rows per thread.  `bm_mma_pair_kernel` (opt-in) is the
+// `cta_group::2` form of the same product.
 #include <cuda/ptx>
 #include <cuda_bf16.h>
 
