@@ -871,7 +871,15 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
 // epilogues.  Verified in isolation by tools/umma_pair_probe.cu (bit-exact, 128 cycles per M256 N256 K32).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPairAStages = 16;       // 16 TMEM columns each (128 rows x 64 int8), after the 256 accumulator columns
-constexpr int kPairThreads = 320;      // 8 producer / epilogue warps, TMA warp, MMA warp
+#ifndef H2_BM_PAIR_GROUPS
+#define H2_BM_PAIR_GROUPS 2
+#endif
+// producer groups of 4 warps per CTA; group k expands the units with it % kPairGroups == k.  A warp cannot have two
+// tcgen05.st in flight (tcgen05.wait::st waits for all of them), so the number of groups is the number of units whose
+// stores can be outstanding at once — a build-time knob (2 or 4) for the next round's measurements.
+constexpr int kPairGroups = H2_BM_PAIR_GROUPS;
+static_assert(kPairGroups == 2 || kPairGroups == 4, "H2_BM_PAIR_GROUPS");
+constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;   // producer / epilogue warps, TMA warp, MMA warp
 #ifndef H2_BM_PAIR_B_STAGES
 #define H2_BM_PAIR_B_STAGES 8
 #endif
@@ -952,14 +960,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
     const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);                 // local TMA
     const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kPairBStages);     // multicast commit
     const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kPairBStages);       // multicast commit
-    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kPairBStages + 1);  // leader only: 16 epilogue warps
+    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kPairBStages + 1);  // leader only: both CTAs' epilogue warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1;
     const int seg_begin = p.cta_seg_ptr[pair], seg_end = p.cta_seg_ptr[pair + 1];
     const int n_work = seg_end - seg_begin;
-    constexpr int kTmaWarp = 8, kMmaWarp = 9;
+    constexpr int kTmaWarp = 4 * kPairGroups, kMmaWarp = 4 * kPairGroups + 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kAStg; ++s) {
@@ -971,7 +979,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
             mbar_init(bar_empty_b + 8 * s, 1);
         }
         mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 16);
+        mbar_init(bar_acc_empty, 2 * 4 * kPairGroups);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // the same warp of both CTAs
@@ -1051,10 +1059,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
             const BmSegment sg = p.seg[seg_begin + w];
             bool pending = false;
             uint32_t pending_sa = 0;
-            const int skip = (int)((uint32_t)(grp + 2 - (int)(it % 2)) % 2);
+            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it % kPairGroups)) % kPairGroups);
             const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
             it += skip;
-            for (int u = sg.unit_begin + skip; u < sg.unit_end; u += 2, it += 2) {
+            for (int u = sg.unit_begin + skip; u < sg.unit_end; u += kPairGroups, it += kPairGroups) {
                 const uint32_t sb = it % kPairBStages, pb = (it / kPairBStages) & 1;
                 mbar_wait(bar_full_b + 8 * sb, pb);
                 const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
@@ -1091,15 +1099,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
             // ---- epilogue: warp = (lane quarter, 64-feature sub-group = which half of the 256 accumulator columns) ----
             mbar_wait(bar_acc_full, acc_it & 1);
             tc_fence_after();
-            const int sub = grp;                                   // columns [128 sub, 128 sub + 128): digits of group 2 pg + sub
+            const int sub = grp & 1;                               // columns [128 sub, 128 sub + 128): digits of group 2 pg + sub
+            constexpr int kParts = kPairGroups / 2;                // warps sharing (quarter, sub) split the 32-column blocks
+            const int part = grp >> 1;
             const int g = 2 * sg.group + sub;
             const int64_t grow = (int64_t)sg.tile * kTileRows + rank * 128 + r;
             const bool row_ok = grow < p.n_rows;
             const float scale = __ldg(p.xstep) * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
             const int valid_cols = sg.partial_slot < 0 ? max(0, min(DG, p.d - g * DG)) : DG;
-            float *stage = stage_gen + warp * (32 * kStageStride);
+            float *stage = stage_gen + (warp & 7) * (32 * kStageStride);
 #pragma unroll 1
-            for (int c0 = 0; c0 < DG; c0 += 32) {
+            for (int c0 = part * 32; c0 < DG; c0 += 32 * kParts) {
                 uint32_t acc[S][32];
 #pragma unroll
                 for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_lane + sub * NBH + s * DG + c0);
@@ -1121,7 +1131,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
                 constexpr int kLanesPerRow = DG / 4, kRowsPerInstr = 32 / kLanesPerRow;
                 const int rr = lane / kLanesPerRow, c = (lane % kLanesPerRow) * 4;
                 const int row0 = (int)rank * 128 + quarter * 32;
-                const bool col_ok = c + 4 <= valid_cols;
+                const bool col_ok = c + 4 <= valid_cols && (kParts == 1 || (c / 32) % kParts == part);
 #pragma unroll
                 for (int j = 0; j < 32; j += kRowsPerInstr) {
                     const int row = j + rr;
