@@ -1529,7 +1529,7 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     const bool i8 = splits_i8(splits);
     H2_REQUIRE(h->bit_order == (i8 ? 1 : 0), H2_ERR_INVALID, "h2_bm_spmm_f32: plan was filled with bit order %d, splits=%d needs %d "
                "(h2_bm_fill_order)", h->bit_order, splits, i8 ? 1 : 0);
-    H2_REQUIRE(!i8 || h->n_cols <= (1 << 18), H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: int8 digits need n_cols <= 2^18 (int32 accumulators)");
+    H2_REQUIRE(!i8 || h->n_cols <= (1 << 17), H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: int8 digits need n_cols <= 2^17 (int32 accumulators: 2^17 terms of at most 64 * 128)");
     const int dg = dg_for(d, splits);
     const int n_groups = groups_for(d, dg);
     H2_REQUIRE(n_groups <= 8, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups (max 8): split the columns", d, n_groups);

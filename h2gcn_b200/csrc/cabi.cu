@@ -159,7 +159,7 @@ static bool splits_ok(int32_t s) { return s == 2 || s == 3 || s == H2_SPLITS_I8X
 static bool splits_is_i8(int32_t s) { return s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
 
 static bool pick_bitmap(int32_t mode, int32_t splits, bool has_dinv, int64_t nnz, int32_t n_rows, int32_t n_cols) {
-    if (splits_is_i8(splits) && n_cols > (1 << 18)) return false;   // int32 accumulators: <= 2^18 terms of |64 * 127|
+    if (splits_is_i8(splits) && n_cols > (1 << 17)) return false;   // int32 accumulators: <= 2^17 terms of at most 64 * 128
     const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
     // measured crossover on B200 (d = 128): a 256x64 unit costs ~6.9 ns on the tensor cores, a CSR entry ~41 ps of
     // gather => the bitmap wins above ~170 entries per unit, i.e. ~1 % density

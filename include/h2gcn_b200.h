@@ -140,7 +140,7 @@ int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_dev, int32_t 
  *                      matrix, a power-of-two block exponent 2^t, t in 0..6, per 4 consecutive rows of X' carried by
  *                      the 0/1 operand as 0/2^t), kind::i8 at twice the bf16 rate, EXACT int32 accumulation, one fp32
  *                      rounding in the epilogue.  Measured against the fp32 oracle: ~4e-5 of max-abs (I8X2), ~2e-7 (I8X3).
- *                      The bitmaps of an int8 plan use bit order 1 (h2_bm_fill_order); n_cols <= 2^18.
+ *                      The bitmaps of an int8 plan use bit order 1 (h2_bm_fill_order); n_cols <= 2^17 (int32 accumulators).
  *
  * Build (once per graph, two phases like hop2): h2_bm_count SYNCHRONISES and returns the number of non-empty
  * 256x64 units; the caller allocates h2_bm_plan_dev_bytes(); h2_bm_fill SYNCHRONISES (it builds the stream-K
