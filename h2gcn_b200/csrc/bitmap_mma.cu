@@ -870,7 +870,17 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
 // free" / "accumulator full" commits are multicast to both CTAs, its "accumulator drained" barrier collects both
 // epilogues.  Verified in isolation by tools/umma_pair_probe.cu (bit-exact, 128 cycles per M256 N256 K32).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kPairAStages = 16;       // 16 TMEM columns each (128 rows x 64 int8), after the 256 accumulator columns
+#ifndef H2_BM_PAIR_UNITS
+#define H2_BM_PAIR_UNITS 1
+#endif
+// Units per A hand-over (1 or 2).  One `tcgen05.st` -> `wait::st` -> arrive -> MMA-wait round trip costs the same
+// several hundred cycles whatever it carries; with 2 a producer thread expands the rows of TWO consecutive units of its
+// segment into one 32-column store and the MMA thread issues both units' MMAs behind one barrier wait (the two units
+// keep their own B stages: the K order of the accumulation is free).  Build-time knob for the next round; 1 = the
+// measured kernel.
+constexpr int kPairUnits = H2_BM_PAIR_UNITS;
+static_assert(kPairUnits == 1 || kPairUnits == 2, "H2_BM_PAIR_UNITS");
+constexpr int kPairAStages = 16 / kPairUnits;   // 16 x kPairUnits TMEM columns each (128 rows x 64 int8 per unit), after the 256 accumulator columns
 #ifndef H2_BM_PAIR_GROUPS
 #define H2_BM_PAIR_GROUPS 2
 #endif
@@ -883,6 +893,10 @@ constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;   // producer / epilogu
 #ifndef H2_BM_PAIR_B_STAGES
 #define H2_BM_PAIR_B_STAGES 8
 #endif
+// The arrive of a hand-over is deferred until its producer group has expanded its NEXT hand-over (kPairGroups later),
+// so the units of both must be resident at once: fewer stages than this deadlocks.
+static_assert(H2_BM_PAIR_B_STAGES >= kPairUnits * (kPairGroups + 1) + 1, "H2_BM_PAIR_B_STAGES too small for the producer groups");
+static_assert(kPairAStages >= kPairGroups + 2, "A stage ring too small for the producer groups");
 constexpr int kPairBStages = H2_BM_PAIR_B_STAGES;   // B half tiles (9 KB) + bitmap halves (1 KB); up to 14 fit next to the epilogue stage
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -1024,24 +1038,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
     } else if (warp == kMmaWarp) {
         // ===== MMA issuer: the leader's elected lane, for both CTAs =====
         if (rank == 0 && elect_one()) {
-            uint32_t it = 0, acc_it = 0;
+            uint32_t it = 0, sit = 0, acc_it = 0;   // units, hand-overs, accumulator phases so far
             for (int w = 0; w < n_work; ++w) {
                 const BmSegment sg = p.seg[seg_begin + w];
                 mbar_wait_cluster(bar_acc_empty, (acc_it & 1) ^ 1);   // both epilogues have drained the accumulators
                 tc_fence_after();
                 uint32_t acc = 0;
-                for (int u = sg.unit_begin; u < sg.unit_end; ++u, ++it) {
-                    const uint32_t sa = it % kAStg, sb = it % kPairBStages;
-                    mbar_wait_cluster(bar_full_a + 8 * sa, (it / kAStg) & 1);   // both CTAs: A stored (and B landed)
+                for (int u = sg.unit_begin; u < sg.unit_end; u += kPairUnits, ++sit) {
+                    const int cnt = min(kPairUnits, sg.unit_end - u);           // units behind this hand-over
+                    const uint32_t sa = sit % kAStg;
+                    mbar_wait_cluster(bar_full_a + 8 * sa, (sit / kAStg) & 1);   // both CTAs: A stored (and B landed)
                     tc_fence_after();
-                    const uint32_t b0 = smem_base + sb * kBStride;
-                    const uint32_t a0 = tmem_base + kACol0 + sa * 16;
+                    const uint32_t a0 = tmem_base + kACol0 + sa * (16 * kPairUnits);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_i8_ts_pair(tmem_base, a0 + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc, k > 0 ? 1u : acc);
+                    for (int j = 0; j < kPairUnits; ++j) {
+                        if (j < cnt) {
+                            const uint32_t b0 = smem_base + ((it + j) % kPairBStages) * kBStride;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_i8_ts_pair(tmem_base, a0 + j * 16 + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc, (j > 0 || k > 0) ? 1u : acc);
+                        }
+                    }
                     acc = 1;
                     umma_commit_pair(bar_empty_a + 8 * sa);
-                    umma_commit_pair(bar_empty_b + 8 * sb);
+#pragma unroll
+                    for (int j = 0; j < kPairUnits; ++j)
+                        if (j < cnt) umma_commit_pair(bar_empty_b + 8 * ((it + j) % kPairBStages));
+                    it += cnt;
                 }
                 umma_commit_pair(bar_acc_full);
                 ++acc_it;
@@ -1054,29 +1077,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
         const int r = quarter * 32 + lane;                       // row inside this CTA's 128-row half
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t full_a_leader = mapa_u32(bar_full_a, 0), acc_empty_leader = mapa_u32(bar_acc_empty, 0);
-        uint32_t it = 0, acc_it = 0;
+        uint32_t it = 0, sit = 0, acc_it = 0;   // units, hand-overs, accumulator phases before this segment
         for (int w = 0; w < n_work; ++w, ++acc_it) {
             const BmSegment sg = p.seg[seg_begin + w];
             bool pending = false;
             uint32_t pending_sa = 0;
-            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it % kPairGroups)) % kPairGroups);
-            const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
-            it += skip;
-            for (int u = sg.unit_begin + skip; u < sg.unit_end; u += kPairGroups, it += kPairGroups) {
-                const uint32_t sb = it % kPairBStages, pb = (it / kPairBStages) & 1;
-                mbar_wait(bar_full_b + 8 * sb, pb);
-                const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
-                const unsigned long long b0 = bits_gen[sb * 128 + r];
-                const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32);
-                uint32_t a[16];
+            const int n_units = sg.unit_end - sg.unit_begin;
+            const int n_hand = (n_units + kPairUnits - 1) / kPairUnits;      // hand-overs of this segment
+            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(sit % kPairGroups)) % kPairGroups);
+            for (int hnd = skip; hnd < n_hand; hnd += kPairGroups) {        // this group's hand-overs
+                const uint32_t hs = sit + (uint32_t)hnd;                     // global hand-over index
+                const uint32_t iu = it + (uint32_t)(hnd * kPairUnits);        // global index of its first unit
+                const int cnt = min(kPairUnits, n_units - hnd * kPairUnits);
+                uint32_t a[16 * kPairUnits];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint4 c = cst[q];
-                    const uint32_t x = q < 4 ? x0 : x1;
-                    a[2 * q] = __funnelshift_r(x, x, c.x) & c.y;
-                    a[2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
+                for (int j = 0; j < kPairUnits; ++j) {
+                    if (j < cnt) {
+                        const uint32_t sb = (iu + j) % kPairBStages, pb = ((iu + j) / kPairBStages) & 1;
+                        mbar_wait(bar_full_b + 8 * sb, pb);
+                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
+                        const unsigned long long b0 = bits_gen[sb * 128 + r];
+                        const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint4 c = cst[q];
+                            const uint32_t x = q < 4 ? x0 : x1;
+                            a[16 * j + 2 * q] = __funnelshift_r(x, x, c.x) & c.y;
+                            a[16 * j + 2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) a[16 * j + q] = 0;   // odd tail: the MMA thread skips these columns
+                    }
                 }
-                const uint32_t sa = it % kAStg, pa = (it / kAStg) & 1;
+                const uint32_t sa = hs % kAStg, pa = (hs / kAStg) & 1;
                 if (pending) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
@@ -1085,11 +1119,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_
                 }
                 mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
                 tc_fence_after();
-                cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 16, a);
+                cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * (16 * kPairUnits), a);
                 pending = true;
                 pending_sa = sa;
             }
-            it = it_end;
+            it += (uint32_t)n_units;
+            sit += (uint32_t)n_hand;
             if (pending) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
