@@ -395,10 +395,13 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and world == 1 and args.mode == "auto":   # measured per arithmetic, for this workload only
         traffic = json.load(open(tp)).get("fused_round_dram_bytes_per_launch", {}).get(_cabi.SPLITS_NAME[args.splits])
+    # arithmetic types on the path: fp32 in / out and on the CSR hops; the tensor-core hops multiply 0/1 by int8 digits
+    # (int32 accumulation, exact) or by bf16 pieces (fp32 accumulation)
+    dtype = "f32" if not g.plan.tensor_idx else ("f32+i8" if args.splits in (_cabi.H2_SPLITS_I8X2, _cabi.H2_SPLITS_I8X3) else "f32+bf16")
     line = {
         "metric": "edges*featdim/sec on fused 2-hop SpMM", "value": value, "unit": "edges*featdim/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"uniform random graph |V|={n} |E|={E_PER_GPU * world} d={d} fp32 "
                                f"({'factored dinv' if args.factored else 'explicit fp32'} adjacency values), seed 0, "
                                f"rows sharded over {world} GPU(s)",
