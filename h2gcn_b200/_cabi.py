@@ -22,10 +22,12 @@ SPLITS_NAME = {2: "2 bf16 pieces", 3: "3 bf16 pieces", H2_SPLITS_I8X2: "2 int8 d
                H2_SPLITS_I8X3: "3 int8 digits + block exponents"}
 
 
-# Default arithmetic of the tensor-core path: int8 digits with block exponents (exact int32 accumulation, ~8e-6 of max-abs
-# against the fp32 oracle at the north-star point, bar 1e-4; 13 % faster per round than 2 bf16 pieces because the B
-# tiles are half the bytes and the round is L2-bandwidth bound).  Override with H2GCN_SPLITS=2|3|i8x2|i8x3.
-DEFAULT_SPLITS = os.environ.get("H2GCN_SPLITS", "i8x2")
+# Default arithmetic of the tensor-core path: THREE int8 digits with block exponents — 24 significant bits of X', exact
+# int32 accumulation, one fp32 rounding in the epilogue: as accurate as the fp32 CSR path (3e-7 of max-abs against the
+# fp32 oracle, the reference's own fp32-vs-fp64 error is 2-5e-7), so the model API (forward AND backward) computes at the
+# reference's precision.  "i8x2" (16 bits, ~8e-6 norm-wise, rows far below the global maximum lose relative precision) is
+# an opt-in: H2GCN_SPLITS=2|3|i8x2|i8x3 or HopPlan(splits=...).
+DEFAULT_SPLITS = os.environ.get("H2GCN_SPLITS", "i8x3")
 
 
 def splits_code(splits=None):
@@ -72,6 +74,7 @@ PROTOTYPES = {
     "h2_bm_plan_dev_bytes": (c_sz, [c_i32, c_i32, c_i64]),
     "h2_bm_fill": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "h2_bm_fill_order": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    "h2_bm_max_width": (c_i32, [c_i32]),
     "h2_bm_xpack_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "h2_bm_partial_bytes": (c_sz, [c_vp, c_i32, c_i32]),
     "h2_bm_pack_x_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
@@ -84,6 +87,9 @@ PROTOTYPES = {
                                        ctypes.POINTER(c_vp)]),
     "h2_graph_create_device": (ctypes.c_int, [c_i32, c_i32, c_i32, ctypes.POINTER(HopDesc), ctypes.POINTER(c_i64), c_i32, c_i32,
                                               c_i32, ctypes.POINTER(c_vp)]),
+    "h2_graph_workspace_bytes": (c_sz, [c_vp, c_i32]),
+    "h2_graph_bind_workspace": (ctypes.c_int, [c_vp, c_i32, c_vp, c_sz]),
+    "h2_graph_reserve": (ctypes.c_int, [c_vp, c_i32]),
     "h2_graph_formats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32)]),
     "h2_graph_round_host": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "h2_graph_round": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),

@@ -31,95 +31,16 @@
 //
 // Arithmetics (`splits`, include/h2gcn_b200.h).  The description above is the bf16 one (kind::f16, 2 / 3 pieces of X').
 // The DEFAULT is int8 (`I8 = true`, H2_SPLITS_I8X2 / I8X3): X' as block-fixed-point — one step for the matrix, a block
-// exponent 2^t (t in 0..6) per 4 rows carried by the 0/1 operand as bytes 0 / 2^t, 2 / 3 balanced base-256 digits as
+// exponent 2^t (t in 0..6) per ROW of X' carried by the 0/1 operand as bytes 0 / 2^t, 2 / 3 balanced base-256 digits as
 // the int8 B operand — on `tcgen05.mma kind::i8` (K = 32, twice the bf16 MAC rate, EXACT int32 accumulation; the
 // epilogue converts and scales once).  Differences: bm_absmax_kernel + bm_pack_i8_kernel build the operand (B tiles of
 // [S*DG x 64] bytes, SWIZZLE_64B, + 128 bytes of per-word {rotate, mask} constants); bitmaps in bit order 1 so that
 // an operand word is one rotate + one mask; A stages of 2 x 16 TMEM columns (8 of them); the 8 producer warps form
 // two groups of 4 that take alternate units and expand two rows per thread.  `bm_mma_pair_kernel` (opt-in) is the
 // `cta_group::2` form of the same product.
-#include <cuda/ptx>
-#include <cuda_bf16.h>
-
-#include <algorithm>
-#include <cstdlib>
-#include <cstring>
-#include <type_traits>
-#include <vector>
-
-#include <cub/device/device_scan.cuh>
-
-#include "common.cuh"
+#include "bm_common.cuh"
 
 namespace h2 {
-
-constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B tile
-constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int kAStages = 4;    // A tiles live in TMEM: 4 x (2 halves x 32 columns) next to 2 x 128 accumulator columns
-constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in shared memory
-// sets of 8 A-producer/epilogue warps: 1 for the bf16 kernel (keeps the register footprint small enough for a CSR-gather
-// CTA of the same round to share the SM), 2 for the int8 kernel (a unit is half the MMA time: see the producer loop)
-#ifndef H2_BM_I8_SETS
-#define H2_BM_I8_SETS 1
-#endif
-__host__ __device__ constexpr int bm_producer_sets(bool i8) { return i8 ? H2_BM_I8_SETS : 1; }
-__host__ __device__ constexpr int bm_threads(bool i8) { return (8 * bm_producer_sets(i8) + 2) * 32; }   // producers, TMA warp, MMA warp (last)
-constexpr uint32_t kBmMagic = 0x48324234u;  // "H2B4"
-constexpr int kAStagesMax = 8;   // int8 A tiles are half as wide: up to 8 stages of 32 TMEM columns
-
-// `splits` codes (include/h2gcn_b200.h): 2 / 3 = bf16 pieces; H2_SPLITS_I8X2 / H2_SPLITS_I8X3 = int8 digits with
-// per-4-row block exponents (kind::i8, exact int32 accumulation)
-__host__ __device__ constexpr bool splits_valid(int s) { return s == 2 || s == 3 || s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
-__host__ __device__ constexpr bool splits_i8(int s) { return s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
-__host__ __device__ constexpr int splits_pieces(int s) { return s == H2_SPLITS_I8X2 ? 2 : (s == H2_SPLITS_I8X3 ? 3 : s); }
-// largest magnitude S balanced base-256 digits in [-128, 127] can carry on both signs: 127 * (256^S - 1) / 255
-__host__ __device__ constexpr int i8_range(int S) { return S == 2 ? 32639 : 8355711; }
-constexpr int kI8Levels = 6;          // block exponents t in 0..6: the A operand carries 2^t (<= 64) instead of 1
-constexpr int kI8ConstBytes = 128;    // per B tile: 16 x {rotate amount, byte mask} for the A producers
-constexpr int kI8HeaderBytes = 256;   // xpack header: fp32 quantisation step
-constexpr int kAbsmaxRows = 32;       // rows per CTA of bm_absmax_kernel (8 warps x 4 rows)
-
-// Bit position of column c (0..63) of a unit row.  Order 0: natural.  Order 1 (int8 path): the four columns of an
-// operand word sit 8 bits apart, so that word j = 4 bytes {0, 2^t} comes out of ONE rotate + ONE mask:
-//   bit(c) = 32 * (c / 32) + 8 * (c % 4) + (c % 32) / 4
-__host__ __device__ constexpr int bm_bit_pos(int c, int order) {
-    return order == 0 ? c : 32 * (c / 32) + 8 * (c % 4) + (c % 32) / 4;
-}
-
-struct BmSegment {       // one contiguous run of units inside one (row tile, column group), handled by one CTA
-    int32_t tile;
-    int32_t unit_begin;  // global unit index
-    int32_t unit_end;
-    int32_t partial_slot;  // -1: covers the whole tile -> write Y directly; else index into the partial workspace
-    int32_t group;         // column group (DG features) this segment computes
-    int32_t pad;
-};
-
-struct BmFix {           // one (row tile, column group) whose result is the ordered sum of partial slots
-    int32_t tile;
-    int32_t slot_begin;
-    int32_t slot_end;
-    int32_t group;
-};
-
-constexpr int kNumScheds = 4;   // stream-K schedules for 1, 2, 4, 8 column groups (work items are group-major)
-constexpr int kNumPairScheds = 3;
-struct BmSched {
-    int32_t n_ctas, n_partial_slots, n_fix, pad;
-    int64_t off_seg, off_cta_seg_ptr, off_fix;
-};
-
-struct BmHost {          // host header (caller's bm_host buffer)
-    uint32_t magic;
-    int32_t n_rows, n_cols, n_tiles, n_chunks;
-    int32_t bit_order;   // bm_bit_pos order of the stored bitmaps: 0 (bf16 kernel) / 1 (int8 kernel)
-    int64_t n_units;
-    int64_t nnz;
-    // offsets (bytes) into the device plan buffer
-    int64_t off_unit_chunk, off_bits, off_empty_tiles, n_empty_tiles;
-    BmSched sched[kNumScheds];
-    BmSched sched_pair[kNumPairScheds];   // CTA-pair kernel: <= 74 pairs, 1 / 2 / 4 column groups of 128 features
-};
 
 // ------------------------------------------------------------------------------------------------------------------
 // format construction
@@ -244,224 +165,200 @@ __global__ void gather_rows_kernel(int32_t n_cols, int32_t d4, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // int8 operand (kind::i8): X' = diag(dinv) X as block-fixed-point.
-//   x'[j][c] ~= step * 2^t(j/4) * q[j][c],   q an integer of S balanced base-256 digits (|q| <= i8_range(S)),
-//   step = 2^(e_max - 5) / i8_range(S) for the whole matrix (e_max = exponent of max |x'|), t = block exponent of the
-//   4-row group in 0..6 (groups more than 64x below the maximum keep t = 0 and lose precision gracefully).
-// The 0/1 pattern operand carries 2^t (bm_mma_kernel expands bit -> byte 0 / 2^t), the digits are the int8 B operand,
+//   x'[j][c] ~= step * 2^t(j) * q[j][c],   q an integer of S balanced base-256 digits (|q| <= i8_range(S)),
+//   step = 2^(e_max - 5) / i8_range(S) for the whole matrix (e_max = exponent of max |x'|), t = exponent of ROW j in 0..6
+//   (rows more than 64x below the maximum keep t = 0 and lose one bit per factor 2 below that: with 3 digits a row
+//   10^4 below the maximum still carries 16 bits).  Round 1 used one exponent per 4 rows: a small row sharing a group
+//   with a large one lost up to 6 more bits, visible in a ROW-wise error metric (tests: row_wise_relative_error).
+// The 0/1 pattern operand carries 2^t (the MMA kernels expand bit -> byte 0 / 2^t), the digits are the int8 B operand,
 // the int32 accumulation is exact, and the epilogue applies step * dinv_row once.
-// Pass 1 (bm_absmax_kernel): max |x'| per 4-row group and per CTA (no atomics: deterministic, nothing to reset);
-// also writes the gathered fp32 copy when the input comes as row shards.  Pass 2 (bm_pack_i8_kernel): quantise and
-// write, per 64-row chunk and column group, the K-major SWIZZLE_64B image of the [S*DG x 64] int8 B tile followed by
-// the 16 {rotate, mask} pairs the A producers need for that chunk.
+//
+// ONE cooperative launch (bm_pack_i8_kernel; round 1 used two kernels, 8.5 + 9.3 us): phase 1 loads a [64 rows x 128
+// features] slab per work item (128-bit loads, possibly from PEER memory: the hop-boundary all-gather of a row-sharded
+// round, which also leaves the gathered fp32 copy), scales it by dinv and keeps it in shared memory, and reduces max |x'|
+// per row and per CTA (no atomics on values: deterministic); a grid barrier (arrive / depart counters in the
+// buffer header, self-resetting) makes the global maximum known; phase 2 derives the block exponents, quantises the slab
+// still sitting in shared memory and writes, per 64-row chunk and column group, the K-major SWIZZLE_64B image of the
+// [S*DG x 64] int8 B tile followed by the 16 {rotate, mask} pairs the A producers need for that chunk.  X is read once.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bm_absmax_kernel(int32_t n_cols, int32_t d, const __grid_constant__ PackSrc src,
-                                                        const float *__restrict__ dinv, float *__restrict__ gmax4,
-                                                        float *__restrict__ blockmax, float *__restrict__ xfull,
-                                                        int64_t ld_full) {
-    __shared__ float s_m[8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g4 = blockIdx.x * 8 + warp;          // group of 4 rows
-    const int d4 = d >> 2;
-    float m = 0.f;
-    for (int idx = lane; idx < 4 * d4; idx += 32) {
-        const int j = g4 * 4 + idx / d4, c = idx % d4;
-        if (j < n_cols) {
-            const float4 v = reinterpret_cast<const float4 *>(pack_src_row(src, j))[c];   // plain load: may be peer memory
-            if (xfull) reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full)[c] = v;
-            const float sc = dinv ? __ldg(dinv + j) : 1.f;
-            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x * sc), fabsf(v.y * sc)), fmaxf(fabsf(v.z * sc), fabsf(v.w * sc))));
-        }
-    }
-    m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // non-negative floats order like their bits
-    if (lane == 0) {
-        if (g4 * 4 < n_cols) gmax4[g4] = m;
-        s_m[warp] = m;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float b = s_m[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) b = fmaxf(b, s_m[w]);
-        blockmax[blockIdx.x] = b;
-    }
-}
-
 __device__ __forceinline__ int f32_exponent(float x) { return (int)((__float_as_uint(x) >> 23) & 0xFFu) - 127; }
 
-constexpr int kPackFeat = 32;   // features per CTA of bm_pack_i8_kernel
+constexpr int kPackSlab = 128;     // features per work item of bm_pack_i8_kernel
+constexpr int kPackThreads = 256;
+
+struct I8Header {                  // first kI8HeaderBytes of the packed operand
+    float step;                    // quantisation step of X' (read by the MMA kernels' epilogues)
+    uint32_t pad[3];
+    uint32_t arrive, depart;       // grid barrier of the pack kernel; zero between launches
+};
 
 template <int DG, int S>
-__global__ void __launch_bounds__(128) bm_pack_i8_kernel(int32_t n_cols, int32_t d, int32_t n_groups,
-                                                         const __grid_constant__ PackSrc src, const float *__restrict__ dinv,
-                                                         const float *__restrict__ gmax4, const float *__restrict__ blockmax,
-                                                         int32_t n_blocks, uint8_t *__restrict__ xpack) {
+__global__ void __launch_bounds__(kPackThreads) bm_pack_i8_kernel(int32_t n_cols, int32_t d, int32_t n_groups, int32_t n_slabs,
+                                                                  const __grid_constant__ PackSrc src, const float *__restrict__ dinv,
+                                                                  float *rowmax, float *blockmax, uint8_t *__restrict__ xpack,
+                                                                  float *__restrict__ xfull, int64_t ld_full) {
     constexpr int NB = S * DG;
     constexpr int kTileBytes = NB * 64 + kI8ConstBytes;
-    constexpr int kSlices = DG / kPackFeat;           // CTAs per (chunk, column group)
-    __shared__ float s_x[kChunkCols][kPackFeat + 1];
-    __shared__ float s_red[4];
-    __shared__ int s_t[16];
-    const int chunk = blockIdx.x, j0 = chunk * kChunkCols;
-    const int g = blockIdx.y / kSlices, slice = blockIdx.y % kSlices;
-    const int f0 = g * DG + slice * kPackFeat;        // first feature of this CTA
+    constexpr int V = kPackSlab / 4;
+    __shared__ float s_x[kChunkCols][kPackSlab + 1];
+    __shared__ float s_red[8];
+    __shared__ int s_t[kChunkCols];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // global maximum = max over the CTA maxima of pass 1
-    float gm = 0.f;
-    for (int i = threadIdx.x; i < n_blocks; i += 128) gm = fmaxf(gm, blockmax[i]);
-    gm = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gm)));
-    if (lane == 0) s_red[warp] = gm;
-    // the [64 x 32] slab scaled by dinv (128-bit loads), zero padded
-    for (int idx = threadIdx.x; idx < kChunkCols * (kPackFeat / 4); idx += 128) {
-        const int k = idx / (kPackFeat / 4), f4 = (idx % (kPackFeat / 4)) * 4;
-        const int j = j0 + k;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < n_cols && f0 + f4 < d) {
-            v = *reinterpret_cast<const float4 *>(pack_src_row(src, j) + f0 + f4);
-            const float sc = dinv ? __ldg(dinv + j) : 1.f;
-            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-        }
-        s_x[k][f4] = v.x; s_x[k][f4 + 1] = v.y; s_x[k][f4 + 2] = v.z; s_x[k][f4 + 3] = v.w;
-    }
-    __syncthreads();
-    gm = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    const int eg = gm > 0.f ? max(f32_exponent(gm), -96) : -96;
-    uint8_t *tile = xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes;
-    if (threadIdx.x < 16) {
-        const int g4 = chunk * 16 + threadIdx.x;
-        const float mg = (g4 * 4 < n_cols) ? gmax4[g4] : 0.f;
-        const int t = mg > 0.f ? min(max(f32_exponent(mg) - eg + kI8Levels, 0), kI8Levels) : 0;
-        s_t[threadIdx.x] = t;
-        // word j of an A row = columns 4j..4j+3 = bits 8k + (j % 8) of half j / 8 (bm_bit_pos order 1):
-        // rotate right by (j % 8) - t, keep bit t of every byte
-        if (slice == 0)
-            *reinterpret_cast<uint2 *>(tile + NB * 64 + threadIdx.x * 8) =
-                make_uint2((uint32_t)((threadIdx.x & 7) - t) & 31u, 0x01010101u << t);
-    }
-    if (chunk == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-        *reinterpret_cast<float *>(xpack) = ldexpf(1.f, eg - 5) / (float)i8_range(S);
-    __syncthreads();
-    const float mult = ldexpf((float)i8_range(S), 5 - eg);
-    // thread = (feature fl, 16 consecutive k): S x 16 bytes
-    {
-        const int fl = threadIdx.x % kPackFeat, c16 = threadIdx.x / kPackFeat;
-        uint32_t w[S][4];
+    const int n_chunks = (n_cols + kChunkCols - 1) / kChunkCols;
+    const int n_items = n_chunks * n_slabs;
+    I8Header *hdr = reinterpret_cast<I8Header *>(xpack);
+
+    auto load_slab = [&](int chunk, int slab, bool first_pass) {
+        const int j0 = chunk * kChunkCols, f0 = slab * kPackSlab;
+        constexpr int kPer = kChunkCols * V / kPackThreads;    // 8 float4 per thread: ALL loads are issued before the first use
+        float4 v[kPer];
+        float sc[kPer];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int k = c16 * 16 + e;
-            const float sc = __int_as_float((127 - s_t[k >> 2]) << 23);   // 2^-t
-            int q = __float2int_rn(s_x[k][fl] * (mult * sc));
-#pragma unroll
-            for (int t = S - 1; t >= 0; --t) {        // piece 0 = most significant digit
-                const int dig = ((q + 128) & 255) - 128;
-                q = (q - dig) >> 8;
-                const uint32_t b = (uint32_t)dig & 0xFFu;
-                if (e & 3) w[t][e >> 2] |= b << (8 * (e & 3)); else w[t][e >> 2] = b;
+        for (int i = 0; i < kPer; ++i) {
+            const int idx = threadIdx.x + i * kPackThreads;
+            const int k = idx / V, f4 = (idx % V) * 4;
+            const int j = j0 + k;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[i] = 0.f;
+            if (j < n_cols && f0 + f4 < d) {   // d % 4 == 0: a float4 is either fully inside or fully outside
+                const float *p = (first_pass || !xfull) ? pack_src_row(src, j) + f0 + f4      // plain load: may be peer memory
+                                                        : xfull + (int64_t)j * ld_full + f0 + f4;   // second pass: the local copy
+                v[i] = *reinterpret_cast<const float4 *>(p);
+                sc[i] = dinv ? __ldg(dinv + j) : 1.f;
             }
         }
 #pragma unroll
-        for (int t = 0; t < S; ++t) {
-            const int n = t * DG + slice * kPackFeat + fl;
-            const int off = (n >> 3) * 512 + (n & 7) * 64 + ((c16 ^ ((n >> 1) & 3)) << 4);   // SWIZZLE_64B, 512-byte atoms
-            *reinterpret_cast<uint4 *>(tile + off) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+        for (int i = 0; i < kPer; ++i) {
+            const int idx = threadIdx.x + i * kPackThreads;
+            const int k = idx / V, f4 = (idx % V) * 4;
+            const int j = j0 + k;
+            if (xfull && first_pass && j < n_cols && f0 + f4 < d)
+                *reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full + f0 + f4) = v[i];   // gathered fp32 copy
+            s_x[k][f4] = v[i].x * sc[i]; s_x[k][f4 + 1] = v[i].y * sc[i]; s_x[k][f4 + 2] = v[i].z * sc[i]; s_x[k][f4 + 3] = v[i].w * sc[i];
+        }
+    };
+
+    // ---- phase 1: maxima ----
+    float cta_max = 0.f;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / n_slabs, slab = item % n_slabs;
+        if (item != (int)blockIdx.x) __syncthreads();          // the previous item's slab has been reduced
+        load_slab(chunk, slab, true);
+        __syncthreads();
+#pragma unroll 1
+        for (int ri = 0; ri < kChunkCols / 8; ++ri) {          // warp w: rows 8w .. 8w + 7 of the chunk
+            const int k = 8 * warp + ri;
+            float m = 0.f;
+#pragma unroll
+            for (int c = 0; c < kPackSlab; c += 32) {
+                // non-finite inputs must not poison the one global step: NaN drops out of fmaxf, +-Inf is skipped here
+                // and saturates below (documented divergence: the fp32 CSR path propagates them like the reference)
+                const float a = fabsf(s_x[k][c + lane]);
+                m = fmaxf(m, a <= 3.4e38f ? a : 0.f);
+            }
+            m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));   // non-negative floats order like their bits
+            const int j = chunk * kChunkCols + k;
+            if (lane == 0 && j < n_cols) rowmax[(int64_t)slab * n_cols + j] = m;
+            cta_max = fmaxf(cta_max, m);
         }
     }
-}
+    if (lane == 0) s_red[warp] = cta_max;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) b = fmaxf(b, s_red[w]);
+        blockmax[blockIdx.x] = b;
+        // ---- grid barrier (cooperative launch: every CTA is resident) ----
+        __threadfence();
+        atomicAdd(&hdr->arrive, 1u);
+        while (*reinterpret_cast<volatile uint32_t *>(&hdr->arrive) < gridDim.x) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
 
-// ------------------------------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// One lane of a converged warp, chosen by `elect.sync`: unlike `lane == 0` the compiler knows the region is
-// single-lane and emits straight-line uniform-datapath code for the UTCHMMA / UBLKCP / UTCBAR instructions in it.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred px;\n\t"
-        "elect.sync _|px, 0xffffffff;\n\t"
-        "@px mov.s32 %0, 1;\n\t"
-        "}" : "+r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-// one attempt, no loop: lets a caller start the (slow, ~200-cycle) phase check of the NEXT unit ahead of time
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done;
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// A operand from tensor memory (128 lanes x 8 columns of packed bf16 pairs per K=16 step), B from shared memory.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same for int8 operands (K = 32 per instruction), exact int32 accumulation
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, SWIZZLE_64B operand tile: rows of 64 bytes, 8-row atoms of 512 bytes (verified with tools/umma_i8_probe.cu)
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    // ---- phase 2: global maximum, block exponents, digits ----
+    float gm = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kPackThreads) gm = fmaxf(gm, __ldcg(blockmax + i));
+    gm = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gm)));
+    __syncthreads();                                           // s_red is reused
+    if (lane == 0) s_red[warp] = gm;
+    __syncthreads();
+    gm = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, s_red[w]);
+    const int eg = gm > 0.f ? max(f32_exponent(gm), -96) : -96;
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->step = ldexpf(1.f, eg - 5) / (float)i8_range(S);
+    const float mult = ldexpf((float)i8_range(S), 5 - eg);
+    constexpr int kTilesPerSlab = kPackSlab / DG;              // column groups (B tiles) one slab feeds
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / n_slabs, slab = item % n_slabs;
+        if (n_items > (int)gridDim.x) {                        // several items per CTA: the slab is no longer in shared memory
+            __syncthreads();
+            load_slab(chunk, slab, false);
+        }
+        if (threadIdx.x < kChunkCols) {                        // block exponent of every row of the chunk
+            const int j = chunk * kChunkCols + threadIdx.x;
+            float mg = 0.f;
+            if (j < n_cols)
+                for (int sl = 0; sl < n_slabs; ++sl) mg = fmaxf(mg, __ldcg(rowmax + (int64_t)sl * n_cols + j));
+            s_t[threadIdx.x] = mg > 0.f ? min(max(f32_exponent(mg) - eg + kI8Levels, 0), kI8Levels) : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            // word j of an A row = columns 4j..4j+3 = bits 8b + (j % 8) of half j / 8 (bm_bit_pos order 1).  The A
+            // producers rotate right by j % 8 (bit b -> bit 0 of byte b), spread every bit over its byte (x 0xFF) and keep
+            // bit t(4j + b) of byte b: the mask below.  Every B tile of the chunk carries a copy.
+            const int j = threadIdx.x;
+            const uint32_t mask = (1u << s_t[4 * j]) | (1u << (8 + s_t[4 * j + 1])) | (1u << (16 + s_t[4 * j + 2])) | (1u << (24 + s_t[4 * j + 3]));
+            for (int tl = 0; tl < kTilesPerSlab; ++tl) {
+                const int g = slab * kTilesPerSlab + tl;
+                if (g < n_groups)
+                    *reinterpret_cast<uint2 *>(xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes + NB * 64 + j * 8) =
+                        make_uint2((uint32_t)(j & 7), mask);
+            }
+        }
+        // thread = (32-feature slice, feature fl, 16 consecutive k): S x 16 bytes per slice visit
+        const int fl = threadIdx.x & 31, c16 = (threadIdx.x >> 5) & 3, half = threadIdx.x >> 7;
+#pragma unroll 1
+        for (int sl = half; sl < kPackSlab / 32; sl += 2) {
+            const int f = sl * 32 + fl;                         // feature inside the slab
+            const int g = (slab * kPackSlab + f) / DG;          // column group (B tile)
+            if (g >= n_groups) continue;
+            uint8_t *tile = xpack + kI8HeaderBytes + ((int64_t)chunk * n_groups + g) * kTileBytes;
+            const int fg = (slab * kPackSlab + f) % DG;         // feature inside the group
+            uint32_t w[S][4];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int k = c16 * 16 + e;
+                const float sc = __int_as_float((127 - s_t[k]) << 23);   // 2^-t of row k
+                float tq = s_x[k][f] * (mult * sc);
+                tq = tq != tq ? 0.f : fminf(fmaxf(tq, -(float)i8_range(S)), (float)i8_range(S));   // NaN -> 0, +-Inf saturates
+                int q = __float2int_rn(tq);
+#pragma unroll
+                for (int t = S - 1; t >= 0; --t) {        // piece 0 = most significant digit
+                    const int dig = ((q + 128) & 255) - 128;
+                    q = (q - dig) >> 8;
+                    const uint32_t b = (uint32_t)dig & 0xFFu;
+                    if (e & 3) w[t][e >> 2] |= b << (8 * (e & 3)); else w[t][e >> 2] = b;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+                const int n = t * DG + fg;
+                const int off = (n >> 3) * 512 + (n & 7) * 64 + ((c16 ^ ((n >> 1) & 3)) << 4);   // SWIZZLE_64B, 512-byte atoms
+                *reinterpret_cast<uint4 *>(tile + off) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+            }
+        }
+    }
+    // ---- depart: the last CTA re-arms the barrier for the next launch ----
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&hdr->depart, 1u) == gridDim.x - 1) {
+            hdr->arrive = 0;
+            hdr->depart = 0;
+            __threadfence();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -725,9 +622,8 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                     if (!I8 || !ready) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(0); }
                     if ((warp & 3) == 0 && lane == 0) BM_T2(1, it);
                     if constexpr (I8) {
-                        // word j = columns 4j..4j+3 as bytes 0 / 2^t: the bits sit 8 apart (bm_bit_pos order 1), so a
-                        // rotate brings them to bit t of each byte and a mask keeps them; {rotate, mask} per word ride
-                        // behind the B tile (the block exponent t belongs to the chunk's rows of X').
+                        // word j = columns 4j..4j+3 as bytes 0 / 2^t(column): i8_expand_word; {rotate, mask} per word
+                        // ride behind the B tile (the exponents t belong to the chunk's rows of X').
                         const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NB * 64);
                         const unsigned long long b0 = bits_gen[sb * kTileRows + quarter * 32 + lane];
                         const unsigned long long b1 = bits_gen[sb * kTileRows + 128 + quarter * 32 + lane];
@@ -738,10 +634,10 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                         for (int q = 0; q < 8; ++q) {
                             const uint4 c = cst[q];
                             const uint32_t x = q < 4 ? x0 : x1, y = q < 4 ? y0 : y1;
-                            a[2 * q] = __funnelshift_r(x, x, c.x) & c.y;
-                            a[2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
-                            a[16 + 2 * q] = __funnelshift_r(y, y, c.x) & c.y;       // half 1: the next 16 TMEM columns
-                            a[16 + 2 * q + 1] = __funnelshift_r(y, y, c.z) & c.w;
+                            a[2 * q] = i8_expand_word(x, c.x, c.y);
+                            a[2 * q + 1] = i8_expand_word(x, c.z, c.w);
+                            a[16 + 2 * q] = i8_expand_word(y, c.x, c.y);       // half 1: the next 16 TMEM columns
+                            a[16 + 2 * q + 1] = i8_expand_word(y, c.z, c.w);
                         }
                     } else {
                         const unsigned long long bits = bits_gen[sb * kTileRows + r];
@@ -860,335 +756,6 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// CTA-pair form of the int8 kernel (i8x2, d > 64): `tcgen05.mma.cta_group::2`, M = 256 = 128 rows per CTA, N = 256 = all
-// 2 digits x 128 features of a 128-feature column group.  CTA r of the pair owns rows [128 r, 128 r + 128) of a 256-row
-// tile: it loads ITS half of the unit's bitmap (1 KB) and ITS half of the B tile — the [128 x 64] tile of the 64-feature
-// group 2 pg + r, so the packed operand is the one the single-CTA kernel uses — and expands every bitmap row ONCE (the
-// single-CTA kernel visits a unit once per 64-feature group: twice).  The leader (rank 0) issues the MMAs for both CTAs;
-// its "A ready" barrier collects the producer warps of both CTAs (remote `mbarrier.arrive` through `mapa`), the "stage
-// free" / "accumulator full" commits are multicast to both CTAs, its "accumulator drained" barrier collects both
-// epilogues.  Verified in isolation by tools/umma_pair_probe.cu (bit-exact, 128 cycles per M256 N256 K32).
-// ------------------------------------------------------------------------------------------------------------------
-#ifndef H2_BM_PAIR_UNITS
-#define H2_BM_PAIR_UNITS 1
-#endif
-// Units per A hand-over (1 or 2).  One `tcgen05.st` -> `wait::st` -> arrive -> MMA-wait round trip costs the same
-// several hundred cycles whatever it carries; with 2 a producer thread expands the rows of TWO consecutive units of its
-// segment into one 32-column store and the MMA thread issues both units' MMAs behind one barrier wait (the two units
-// keep their own B stages: the K order of the accumulation is free).  Build-time knob for the next round; 1 = the
-// measured kernel.
-constexpr int kPairUnits = H2_BM_PAIR_UNITS;
-static_assert(kPairUnits == 1 || kPairUnits == 2, "H2_BM_PAIR_UNITS");
-constexpr int kPairAStages = 16 / kPairUnits;   // 16 x kPairUnits TMEM columns each (128 rows x 64 int8 per unit), after the 256 accumulator columns
-#ifndef H2_BM_PAIR_GROUPS
-#define H2_BM_PAIR_GROUPS 2
-#endif
-// producer groups of 4 warps per CTA; group k expands the units with it % kPairGroups == k.  A warp cannot have two
-// tcgen05.st in flight (tcgen05.wait::st waits for all of them), so the number of groups is the number of units whose
-// stores can be outstanding at once — a build-time knob (2 or 4) for the next round's measurements.
-constexpr int kPairGroups = H2_BM_PAIR_GROUPS;
-static_assert(kPairGroups == 2 || kPairGroups == 4, "H2_BM_PAIR_GROUPS");
-constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;   // producer / epilogue warps, TMA warp, MMA warp
-#ifndef H2_BM_PAIR_B_STAGES
-#define H2_BM_PAIR_B_STAGES 8
-#endif
-// The arrive of a hand-over is deferred until its producer group has expanded its NEXT hand-over (kPairGroups later),
-// so the units of both must be resident at once: fewer stages than this deadlocks.
-static_assert(H2_BM_PAIR_B_STAGES >= kPairUnits * (kPairGroups + 1) + 1, "H2_BM_PAIR_B_STAGES too small for the producer groups");
-static_assert(kPairAStages >= kPairGroups + 2, "A stage ring too small for the producer groups");
-constexpr int kPairBStages = H2_BM_PAIR_B_STAGES;   // B half tiles (9 KB) + bitmap halves (1 KB); up to 14 fit next to the epilogue stage
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals come from the peer CTA too
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-
-struct BmPairCfg {
-    static constexpr int S = 2, DG = 64, NBH = S * DG;                    // this CTA's half of the B tile: [128 x 64] int8
-    static constexpr uint32_t kBBytes = NBH * 64 + kI8ConstBytes;
-    static constexpr uint32_t kBStride = (kBBytes + 1023u) & ~1023u;
-    static constexpr uint32_t kBitsBytes = 128 * 8;                       // this CTA's 128 bitmap rows of a unit
-    static constexpr size_t kSmem = (size_t)kPairBStages * (kBStride + kBitsBytes) + 8 * 32 * (DG + 4) * 4 + 1024;
-};
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) bm_mma_pair_kernel(const __grid_constant__ BmParams p) {
-    using Cfg = BmPairCfg;
-    constexpr int S = Cfg::S, DG = Cfg::DG, NBH = Cfg::NBH;
-    constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride, kBitsBytes = Cfg::kBitsBytes;
-    constexpr uint32_t kACol0 = 256, kTmemCols = 512;
-    constexpr int kAStg = kPairAStages;
-    // D int32 | A, B signed int8 | N = 256 | M = 256 (128 rows per CTA)
-    constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint32_t smem_raw_u32 = smem_u32(smem_raw);
-    asm volatile("" : "+r"(smem_raw_u32));
-    const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-    const uint32_t bits_base = smem_base + kPairBStages * kBStride;
-    const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_raw_u32));
-    constexpr int kStageStride = DG + 4;
-    float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kPairBStages * kBitsBytes);
-    __shared__ uint64_t s_bar[2 * kAStg + 2 * kPairBStages + 2];
-    __shared__ uint32_t s_tmem_base;
-    __shared__ int s_chunk[32];
-    uint32_t bar0 = smem_u32(&s_bar[0]);
-    asm volatile("" : "+r"(bar0));
-    const uint32_t bar_full_a = bar0;                                   // leader only: 8 producer warps (4 of each CTA)
-    const uint32_t bar_empty_a = bar0 + 8 * kAStg;                      // multicast commit
-    const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);                 // local TMA
-    const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kPairBStages);     // multicast commit
-    const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kPairBStages);       // multicast commit
-    const uint32_t bar_acc_empty = bar0 + 8 * (2 * kAStg + 2 * kPairBStages + 1);  // leader only: both CTAs' epilogue warps
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1;
-    const int seg_begin = p.cta_seg_ptr[pair], seg_end = p.cta_seg_ptr[pair + 1];
-    const int n_work = seg_end - seg_begin;
-    constexpr int kTmaWarp = 4 * kPairGroups, kMmaWarp = 4 * kPairGroups + 1;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kAStg; ++s) {
-            mbar_init(bar_full_a + 8 * s, 8);
-            mbar_init(bar_empty_a + 8 * s, 1);
-        }
-        for (int s = 0; s < kPairBStages; ++s) {
-            mbar_init(bar_full_b + 8 * s, 1);
-            mbar_init(bar_empty_b + 8 * s, 1);
-        }
-        mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 2 * 4 * kPairGroups);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {   // the same warp of both CTAs
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                     "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
-    tc_fence_after();
-    const uint32_t tmem_base = s_tmem_base;
-
-    if (warp == kTmaWarp) {
-        // ===== TMA producer: this CTA's half of the B tile (+ constants) and of the unit's bitmap =====
-        uint32_t it = 0;
-        for (int w = 0; w < n_work; ++w) {
-            const BmSegment sg = p.seg[seg_begin + w];
-            const int g = 2 * sg.group + (int)rank;        // 64-feature group whose [128 x 64] tile is this CTA's half
-            int nxt = sg.unit_begin + lane < sg.unit_end ? p.unit_chunk[sg.unit_begin + lane] : 0;
-            for (int u0 = sg.unit_begin; u0 < sg.unit_end; u0 += 32) {
-                s_chunk[lane] = nxt;
-                __syncwarp();
-                if (u0 + 32 + lane < sg.unit_end) nxt = p.unit_chunk[u0 + 32 + lane];
-                const int cnt = min(32, sg.unit_end - u0);
-                if (elect_one()) {
-                    for (int k = 0; k < cnt; ++k) {
-                        const int chunk = s_chunk[k];
-                        const uint32_t st = (it + k) % kPairBStages, ph = ((it + k) / kPairBStages) & 1;
-                        mbar_wait(bar_empty_b + 8 * st, ph ^ 1);
-                        mbar_arrive_expect_tx(bar_full_b + 8 * st, kBBytes + kBitsBytes);
-                        const uint4 *src = p.xpack + ((int64_t)chunk * p.n_groups + g) * (kBBytes / 16);
-                        bulk_copy_g2s(smem_base + st * kBStride, src, kBBytes, bar_full_b + 8 * st);
-                        bulk_copy_g2s(bits_base + st * kBitsBytes, p.bits + (int64_t)(u0 + k) * kTileRows + rank * 128, kBitsBytes,
-                                      bar_full_b + 8 * st);
-                    }
-                }
-                it += cnt;
-                __syncwarp();
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // ===== MMA issuer: the leader's elected lane, for both CTAs =====
-        if (rank == 0 && elect_one()) {
-            uint32_t it = 0, sit = 0, acc_it = 0;   // units, hand-overs, accumulator phases so far
-            for (int w = 0; w < n_work; ++w) {
-                const BmSegment sg = p.seg[seg_begin + w];
-                mbar_wait_cluster(bar_acc_empty, (acc_it & 1) ^ 1);   // both epilogues have drained the accumulators
-                tc_fence_after();
-                uint32_t acc = 0;
-                for (int u = sg.unit_begin; u < sg.unit_end; u += kPairUnits, ++sit) {
-                    const int cnt = min(kPairUnits, sg.unit_end - u);           // units behind this hand-over
-                    const uint32_t sa = sit % kAStg;
-                    mbar_wait_cluster(bar_full_a + 8 * sa, (sit / kAStg) & 1);   // both CTAs: A stored (and B landed)
-                    tc_fence_after();
-                    const uint32_t a0 = tmem_base + kACol0 + sa * (16 * kPairUnits);
-#pragma unroll
-                    for (int j = 0; j < kPairUnits; ++j) {
-                        if (j < cnt) {
-                            const uint32_t b0 = smem_base + ((it + j) % kPairBStages) * kBStride;
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                umma_i8_ts_pair(tmem_base, a0 + j * 16 + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc, (j > 0 || k > 0) ? 1u : acc);
-                        }
-                    }
-                    acc = 1;
-                    umma_commit_pair(bar_empty_a + 8 * sa);
-#pragma unroll
-                    for (int j = 0; j < kPairUnits; ++j)
-                        if (j < cnt) umma_commit_pair(bar_empty_b + 8 * ((it + j) % kPairBStages));
-                    it += cnt;
-                }
-                umma_commit_pair(bar_acc_full);
-                ++acc_it;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===== A producers (4-warp groups on alternate units, one bitmap row per thread), then epilogue =====
-        const int grp = warp >> 2, quarter = warp & 3;
-        const int r = quarter * 32 + lane;                       // row inside this CTA's 128-row half
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t full_a_leader = mapa_u32(bar_full_a, 0), acc_empty_leader = mapa_u32(bar_acc_empty, 0);
-        uint32_t it = 0, sit = 0, acc_it = 0;   // units, hand-overs, accumulator phases before this segment
-        for (int w = 0; w < n_work; ++w, ++acc_it) {
-            const BmSegment sg = p.seg[seg_begin + w];
-            bool pending = false;
-            uint32_t pending_sa = 0;
-            const int n_units = sg.unit_end - sg.unit_begin;
-            const int n_hand = (n_units + kPairUnits - 1) / kPairUnits;      // hand-overs of this segment
-            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(sit % kPairGroups)) % kPairGroups);
-            for (int hnd = skip; hnd < n_hand; hnd += kPairGroups) {        // this group's hand-overs
-                const uint32_t hs = sit + (uint32_t)hnd;                     // global hand-over index
-                const uint32_t iu = it + (uint32_t)(hnd * kPairUnits);        // global index of its first unit
-                const int cnt = min(kPairUnits, n_units - hnd * kPairUnits);
-                uint32_t a[16 * kPairUnits];
-#pragma unroll
-                for (int j = 0; j < kPairUnits; ++j) {
-                    if (j < cnt) {
-                        const uint32_t sb = (iu + j) % kPairBStages, pb = ((iu + j) / kPairBStages) & 1;
-                        mbar_wait(bar_full_b + 8 * sb, pb);
-                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NBH * 64);
-                        const unsigned long long b0 = bits_gen[sb * 128 + r];
-                        const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint4 c = cst[q];
-                            const uint32_t x = q < 4 ? x0 : x1;
-                            a[16 * j + 2 * q] = __funnelshift_r(x, x, c.x) & c.y;
-                            a[16 * j + 2 * q + 1] = __funnelshift_r(x, x, c.z) & c.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) a[16 * j + q] = 0;   // odd tail: the MMA thread skips these columns
-                    }
-                }
-                const uint32_t sa = hs % kAStg, pa = (hs / kAStg) & 1;
-                if (pending) {
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * pending_sa);
-                }
-                mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
-                tc_fence_after();
-                cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * (16 * kPairUnits), a);
-                pending = true;
-                pending_sa = sa;
-            }
-            it += (uint32_t)n_units;
-            sit += (uint32_t)n_hand;
-            if (pending) {
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * pending_sa);
-            }
-            // ---- epilogue: warp = (lane quarter, 64-feature sub-group = which half of the 256 accumulator columns) ----
-            mbar_wait(bar_acc_full, acc_it & 1);
-            tc_fence_after();
-            const int sub = grp & 1;                               // columns [128 sub, 128 sub + 128): digits of group 2 pg + sub
-            constexpr int kParts = kPairGroups / 2;                // warps sharing (quarter, sub) split the 32-column blocks
-            const int part = grp >> 1;
-            const int g = 2 * sg.group + sub;
-            const int64_t grow = (int64_t)sg.tile * kTileRows + rank * 128 + r;
-            const bool row_ok = grow < p.n_rows;
-            const float scale = __ldg(p.xstep) * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
-            const int valid_cols = sg.partial_slot < 0 ? max(0, min(DG, p.d - g * DG)) : DG;
-            float *stage = stage_gen + (warp & 7) * (32 * kStageStride);
-#pragma unroll 1
-            for (int c0 = part * 32; c0 < DG; c0 += 32 * kParts) {
-                uint32_t acc[S][32];
-#pragma unroll
-                for (int s = 0; s < S; ++s) cuda::ptx::tcgen05_ld_32x32b(acc[s], t_lane + sub * NBH + s * DG + c0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int q = 0; q < 32; q += 4) {
-                    float4 o;
-                    float *po = &o.x;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)   // digits, most significant first
-                        po[e] = fmaf((float)(int32_t)acc[0][q + e], 256.f, (float)(int32_t)acc[1][q + e]) * scale;
-                    *reinterpret_cast<float4 *>(stage + lane * kStageStride + c0 + q) = o;
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(acc_empty_leader);   // drained: the next segment's MMAs may start
-            {
-                constexpr int kLanesPerRow = DG / 4, kRowsPerInstr = 32 / kLanesPerRow;
-                const int rr = lane / kLanesPerRow, c = (lane % kLanesPerRow) * 4;
-                const int row0 = (int)rank * 128 + quarter * 32;
-                const bool col_ok = c + 4 <= valid_cols && (kParts == 1 || (c / 32) % kParts == part);
-#pragma unroll
-                for (int j = 0; j < 32; j += kRowsPerInstr) {
-                    const int row = j + rr;
-                    const float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + c);
-                    const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
-                    float *drow = sg.partial_slot < 0 ? p.Y + gr * p.ldy + (int64_t)g * DG
-                                                       : p.partial + ((int64_t)sg.partial_slot * kTileRows + row0 + row) * (2 * DG) + sub * DG;
-                    if (col_ok && (sg.partial_slot >= 0 || gr < p.n_rows)) *reinterpret_cast<float4 *>(drow + c) = v;
-                }
-            }
-            __syncwarp();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();   // no CTA frees tensor memory or exits while its peer can still signal it
-    if (warp == kMmaWarp) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 // fix-up: Y[tile rows, group columns] = sum over the partial slots of that (tile, group), ascending slot order
 // (deterministic).  One thread per output float4; grid = (256 * DG/4 / 256, n_fix).
 template <int DG>
@@ -1236,30 +803,60 @@ static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // column-group width: S*DG is the UMMA N (<= 256), two accumulators of S*DG columns must fit the 512 TMEM columns
 // column groups are rounded up to a power of two (1, 2, 4, 8): one schedule per count; padding groups compute zeros
 static int groups_for(int d, int dg) { int g = (d + dg - 1) / dg, p2 = 1; while (p2 < g) p2 <<= 1; return p2; }
-static int dg_for(int d, int splits) { return (d <= 32 || splits == 3) ? 32 : 64; }   // int8: 64 for both digit counts
+// int8: at least the two FH-feature halves of one pair-kernel group (a zero tile for d <= 32)
+static int groups_for_splits(int d, int dg, int splits) { const int g = groups_for(d, dg); return splits_i8(splits) ? std::max(2, g) : g; }
+// features per packed B tile: 32 for 3 bf16 pieces and narrow rounds; int8 rounds use 32 up to d = 64 (the two halves of
+// the pair kernel's 64-feature group) and 64 above
+static int dg_for(int d, int splits) { return (d <= 32 || splits == 3 || (splits_i8(splits) && d <= 64)) ? 32 : 64; }
 static size_t i8_tile_bytes(int dg, int splits) { return (size_t)splits_pieces(splits) * dg * 64 + kI8ConstBytes; }
-struct I8Layout {   // int8 xpack buffer: header | tiles | gmax4 [ceil(n_cols/4)] | blockmax [n_blocks]
-    int64_t n_chunks, n_groups, n_g4, n_blocks;
+struct I8Layout {   // int8 xpack buffer: header | tiles | rowmax [n_slabs][n_cols] | blockmax [kPackMaxCtas]
+    int64_t n_chunks, n_groups, n_slabs;
     size_t off_gmax4, off_blockmax, total;
 };
+constexpr int kPackMaxCtas = kNumSms * 8;
 static I8Layout i8_layout(int32_t n_cols, int32_t d, int32_t splits) {
     I8Layout L;
     const int dg = dg_for(d, splits);
     L.n_chunks = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
-    L.n_groups = groups_for(d, dg);
-    L.n_g4 = ((int64_t)n_cols + 3) / 4;
-    L.n_blocks = ((int64_t)n_cols + kAbsmaxRows - 1) / kAbsmaxRows;
+    L.n_groups = groups_for_splits(d, dg, splits);
+    L.n_slabs = ((int64_t)d + kPackSlab - 1) / kPackSlab;
     L.off_gmax4 = align_up_sz(kI8HeaderBytes + (size_t)(L.n_chunks * L.n_groups) * i8_tile_bytes(dg, splits), 256);
-    L.off_blockmax = L.off_gmax4 + align_up_sz((size_t)L.n_g4 * 4, 256);
-    L.total = L.off_blockmax + align_up_sz((size_t)L.n_blocks * 4, 256) + 256;
+    L.off_blockmax = L.off_gmax4 + align_up_sz((size_t)(L.n_slabs * n_cols) * 4, 256);
+    L.total = L.off_blockmax + align_up_sz((size_t)kPackMaxCtas * 4, 256) + 256;
     return L;
 }
+
+// ---- CTA-pair int8 kernel (bm_pair.cu) ----
+struct BmPairSeg { int32_t tile, unit_begin, unit_end, group, role, slot, fix, pad1; };
+struct BmPairFix { int32_t tile, group, slot_begin, n_slots; };
+struct BmPairParams {
+    const int32_t *unit_chunk; const unsigned long long *bits; const BmPairSeg *seg; const int32_t *cta_seg_ptr;
+    const uint8_t *xpack; const float *xstep; const float *dinv_row; float *Y; float *partial; const BmPairFix *fix;
+    uint32_t *sync; int32_t *status; int32_t n_fix; int64_t ldy; int32_t n_rows, d, n_groups_fh;
+};
+void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int n_pairs_max, std::vector<BmPairSeg> &segs,
+                   std::vector<int32_t> &pair_ptr, std::vector<BmPairFix> &fixes, int *n_slots_out);
+int pair_launch(int S, int fh, int n_pairs, const BmPairParams &p, cudaStream_t st);
+constexpr int kPairMaxSegUnitsHost = 2048;
+static size_t pair_sched_bytes(int64_t nt, int64_t n_units, int ng) {
+    const size_t max_segs = (size_t)(kNumSms / 2 + ng * (nt + 1) + ng * (n_units / kPairMaxSegUnitsHost + 1) + 2);
+    return align_up_sz(max_segs * sizeof(BmPairSeg), 256) + align_up_sz((size_t)(kNumSms / 2 + 2) * 4, 256) +
+           align_up_sz(max_segs * 8, 256) + align_up_sz(max_segs * sizeof(BmPairFix), 256);   // segments, pair_ptr, arrival counters, fix list
+}
+// every int8 round runs on the pair kernel: FH = 32 (d <= 64; a round of <= 32 features computes a zero-padded second
+// half) or FH = 64 features per CTA half, 1 / 2 / 4 column groups of 2*FH features
+static bool pair_applies(int32_t splits, int d) { return splits_i8(splits) && d > 0; }
+static int pair_fh(int d) { return d <= 64 ? 32 : 64; }
+static int pair_groups(int d) { return std::max(2, groups_for(d, pair_fh(d))) / 2; }
 
 }  // namespace h2
 
 using namespace h2;
 
 extern "C" size_t h2_bm_host_bytes(void) { return sizeof(BmHost); }
+
+// widest d one h2_bm_pack_x_f32 / h2_bm_spmm_f32 pair covers (8 column groups); wider rounds go in column slices
+extern "C" int32_t h2_bm_max_width(int32_t splits) { return splits_valid(splits) ? 8 * dg_for(512, splits) : 0; }
 
 extern "C" size_t h2_bm_index_bytes(int32_t n_rows, int32_t n_cols) {
     const int64_t nt = ((int64_t)n_rows + kTileRows - 1) / kTileRows, nc = ((int64_t)n_cols + kChunkCols - 1) / kChunkCols;
@@ -1299,8 +896,8 @@ extern "C" size_t h2_bm_plan_dev_bytes(int32_t n_rows, int32_t n_cols, int64_t n
     size_t b = align_up_sz((size_t)n_units * 4, 256) + align_up_sz((size_t)n_units * kTileRows * 8, 256) +
                align_up_sz((size_t)(nt + 1) * 4, 256) + 1024;
     for (int k = 0; k < kNumScheds; ++k) b += sched_bytes(nt, 1 << k);
-    for (int k = 0; k < kNumPairScheds; ++k) b += sched_bytes(nt, 1 << k);
-    return b;
+    for (int k = 0; k < kNumPairScheds; ++k) b += pair_sched_bytes(nt, n_units, 1 << k);
+    return b + 256;   // + status word
 }
 
 // Phase 2 (SYNCHRONISES): fills the bitmaps and builds the stream-K schedule (segments, partial slots, fix-ups).
@@ -1353,15 +950,14 @@ extern "C" int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *r
         if (tp[q + 1] == tp[q]) empty_tiles.push_back((int32_t)q);
     h->n_empty_tiles = (int64_t)empty_tiles.size();
     if (!empty_tiles.empty()) H2_CUDA(cudaMemcpyAsync(base + h->off_empty_tiles, empty_tiles.data(), empty_tiles.size() * 4, cudaMemcpyHostToDevice, st));
-    std::vector<BmSegment> segs[kNumScheds + kNumPairScheds];
-    std::vector<int32_t> cta_ptr[kNumScheds + kNumPairScheds];
-    std::vector<BmFix> fixes[kNumScheds + kNumPairScheds];
-    for (int k = 0; k < kNumScheds + kNumPairScheds; ++k) {
-        const bool pair = k >= kNumScheds;       // schedules of the CTA-pair kernel: one range per PAIR of CTAs
-        const int ng = 1 << (pair ? k - kNumScheds : k);
+    std::vector<BmSegment> segs[kNumScheds];
+    std::vector<int32_t> cta_ptr[kNumScheds];
+    std::vector<BmFix> fixes[kNumScheds];
+    for (int k = 0; k < kNumScheds; ++k) {
+        const int ng = 1 << k;
         const int64_t total = n_units * ng;
-        const int G = (int)std::min<int64_t>(pair ? kNumSms / 2 : kNumSms, total);
-        BmSched &sc = pair ? h->sched_pair[k - kNumScheds] : h->sched[k];
+        const int G = (int)std::min<int64_t>(kNumSms, total);
+        BmSched &sc = h->sched[k];
         cta_ptr[k].assign(G + 1, 0);
         int n_slots = 0;
         // Every (group, tile) item a CTA enters costs an epilogue (TMEM drain + write-out + pipeline refill, measured
@@ -1416,6 +1012,31 @@ extern "C" int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *r
         H2_CUDA(cudaMemcpyAsync(base + sc.off_cta_seg_ptr, cta_ptr[k].data(), cta_ptr[k].size() * 4, cudaMemcpyHostToDevice, st));
         if (!fixes[k].empty()) H2_CUDA(cudaMemcpyAsync(base + sc.off_fix, fixes[k].data(), fixes[k].size() * sizeof(BmFix), cudaMemcpyHostToDevice, st));
     }
+    // ---- schedules of the CTA-pair kernel (bm_pair.cu): one range per PAIR of CTAs, roles instead of a fix-up pass ----
+    std::vector<BmPairSeg> psegs[kNumPairScheds];
+    std::vector<int32_t> pptr[kNumPairScheds];
+    std::vector<BmPairFix> pfix[kNumPairScheds];
+    const int max_pairs = kNumSms / 2;
+    for (int k = 0; k < kNumPairScheds; ++k) {
+        const int ng = 1 << k;
+        int n_slots = 0;
+        pair_schedule(tp, n_units, ng, max_pairs, psegs[k], pptr[k], pfix[k], &n_slots);
+        const size_t max_segs = (size_t)(kNumSms / 2 + ng * (nt + 1) + ng * (n_units / kPairMaxSegUnitsHost + 1) + 2);
+        H2_REQUIRE(psegs[k].size() <= max_segs && pfix[k].size() <= max_segs, H2_ERR_UNSUPPORTED, "h2_bm_fill: pair schedule table overflow");
+        BmSched &sc = h->sched_pair[k];
+        sc.n_ctas = (int)pptr[k].size() - 1; sc.n_partial_slots = n_slots; sc.n_fix = (int)pfix[k].size();
+        sc.off_seg = off;         off += align_up_sz(max_segs * sizeof(BmPairSeg), 256);
+        sc.off_cta_seg_ptr = off; off += align_up_sz((size_t)(kNumSms / 2 + 2) * 4, 256);
+        const size_t cnt_bytes = align_up_sz(max_segs * 8, 256);
+        sc.off_fix = off;         off += cnt_bytes + align_up_sz(max_segs * sizeof(BmPairFix), 256);   // arrival counters (zero between launches), then the fix list
+        if (!psegs[k].empty()) H2_CUDA(cudaMemcpyAsync(base + sc.off_seg, psegs[k].data(), psegs[k].size() * sizeof(BmPairSeg), cudaMemcpyHostToDevice, st));
+        H2_CUDA(cudaMemcpyAsync(base + sc.off_cta_seg_ptr, pptr[k].data(), pptr[k].size() * 4, cudaMemcpyHostToDevice, st));
+        H2_CUDA(cudaMemsetAsync(base + sc.off_fix, 0, cnt_bytes, st));
+        if (!pfix[k].empty()) H2_CUDA(cudaMemcpyAsync(base + sc.off_fix + cnt_bytes, pfix[k].data(), pfix[k].size() * sizeof(BmPairFix), cudaMemcpyHostToDevice, st));
+    }
+    h->off_status = off; off += 256;
+    H2_CUDA(cudaMemsetAsync(base + h->off_status, 0, 256, st));
+    H2_REQUIRE(off <= bm_dev_bytes, H2_ERR_WORKSPACE, "h2_bm_fill: plan buffer too small (%zu > %zu)", off, bm_dev_bytes);
     H2_CUDA(cudaStreamSynchronize(st));   // the std::vectors go out of scope
     return H2_OK;
 }
@@ -1430,25 +1051,18 @@ extern "C" size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits) {
     return (size_t)(nc * ng * splits * dg * 128) + 256;
 }
 
-// The CTA-pair kernel covers 2 int8 digits and an even number of 64-feature groups (d > 64).  OPT-IN (H2_BM_PAIR=1):
-// bit-identical results and the same round time as the single-CTA kernel on the box (47.7 vs 47.1-48.9 us, profiles/
-// README.md r01f) although every bitmap row is expanded once instead of twice — so the producers' ALU work is not what
-// bounds either kernel; kept as the starting point for the next round.
-static bool pair_kernel_applies(int32_t splits, int n_groups64) {
-    static const bool enabled = [] { const char *e = getenv("H2_BM_PAIR"); return e && e[0] == '1'; }();
-    return enabled && splits == H2_SPLITS_I8X2 && n_groups64 >= 2 && n_groups64 <= 8 && n_groups64 % 2 == 0;
-}
-
 extern "C" size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits) {
     const BmHost *h = (const BmHost *)bm_host;
     if (!h || h->magic != kBmMagic || !splits_valid(splits)) return 0;
+    if (pair_applies(splits, d)) {
+        const int ng = pair_groups(d);
+        if (ng > 4) return 0;
+        return (size_t)h->sched_pair[sched_index(ng)].n_partial_slots * kTileRows * (2 * pair_fh(d)) * 4 + 256;
+    }
     const int dg = dg_for(d, splits);
     const int ng = groups_for(d, dg);
     if (ng > 8) return 0;
-    size_t b = (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4;
-    if (dg == 64 && ng >= 2)   // either kernel may run (the switch is read per call)
-        b = std::max(b, (size_t)h->sched_pair[sched_index(ng / 2)].n_partial_slots * kTileRows * 128 * 4);
-    return b + 256;
+    return (size_t)h->sched[sched_index(ng)].n_partial_slots * kTileRows * dg * 4 + 256;
 }
 
 namespace h2 {
@@ -1470,7 +1084,7 @@ static int fill_src(PackSrc &src, int32_t n_cols, int32_t n_parts, const float *
 // pack from row shards (n_parts pointers + bounds); xfull != nullptr also writes the gathered fp32 matrix
 int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
                   int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
-                  h2_stream_t s) {
+                  h2_stream_t s, bool zero_header) {
     H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && splits_valid(splits) && xpack && ld >= d && ld % 4 == 0,
                H2_ERR_INVALID, "bm_pack: bad argument (d=%d splits=%d)", d, splits);
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
@@ -1480,30 +1094,34 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
     int rc = fill_src(src, n_cols, n_parts, ptrs, bounds, ld);
     if (rc != H2_OK) return rc;
     const int dg = dg_for(d, splits);
-    dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for(d, dg));
+    dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for_splits(d, dg, splits));
     cudaStream_t st = (cudaStream_t)s;
     if (splits_i8(splits)) {
-        // pass 1: maxima (+ the gathered fp32 copy); pass 2: quantise from the local copy when there is one
+        // ONE cooperative launch: maxima (+ the gathered fp32 copy), grid barrier, quantisation from shared memory
         const I8Layout L = i8_layout(n_cols, d, splits);
         H2_REQUIRE(grid.y <= 8, H2_ERR_UNSUPPORTED, "bm_pack: d=%d needs %u column groups (max 8)", d, grid.y);
         uint8_t *xp = (uint8_t *)xpack;
         float *gmax4 = (float *)(xp + L.off_gmax4), *blockmax = (float *)(xp + L.off_blockmax);
-        bm_absmax_kernel<<<(unsigned)L.n_blocks, 256, 0, st>>>(n_cols, d, src, dinv_col, gmax4, blockmax, xfull, ld_full);
-        H2_LAUNCHED("bm_absmax_kernel");
-        PackSrc src2 = src;
-        if (xfull) {
-            const float *one = xfull;
-            const int64_t b2[2] = {0, n_cols};
-            rc = fill_src(src2, n_cols, 1, &one, b2, ld_full);
-            if (rc != H2_OK) return rc;
-        }
+        if (zero_header) H2_CUDA(cudaMemsetAsync(xp, 0, kI8HeaderBytes, st));   // barrier counters of a buffer seen for the first time
         const int S = splits_pieces(splits);
-        const dim3 pgrid(grid.x, grid.y * (dg / kPackFeat));
-#define H2_PACK_I8(DG_, S_) \
-        bm_pack_i8_kernel<DG_, S_><<<pgrid, 128, 0, st>>>(n_cols, d, (int)grid.y, src2, dinv_col, gmax4, blockmax, (int)L.n_blocks, xp)
-        if (dg == 32) { if (S == 2) H2_PACK_I8(32, 2); else H2_PACK_I8(32, 3); }
-        else { if (S == 2) H2_PACK_I8(64, 2); else H2_PACK_I8(64, 3); }
-#undef H2_PACK_I8
+        const void *kern = dg == 32 ? (S == 2 ? (const void *)bm_pack_i8_kernel<32, 2> : (const void *)bm_pack_i8_kernel<32, 3>)
+                                    : (S == 2 ? (const void *)bm_pack_i8_kernel<64, 2> : (const void *)bm_pack_i8_kernel<64, 3>);
+        static int max_ctas[4][64] = {};    // co-resident CTAs per instantiation and device (the grid barrier needs them all resident)
+        int dev = 0;
+        H2_CUDA(cudaGetDevice(&dev));
+        int &cap = max_ctas[(dg == 32 ? 0 : 2) + (S == 2 ? 0 : 1)][dev & 63];
+        if (!cap) {
+            int per_sm = 0, sms = 0;
+            H2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPackThreads, 0));
+            H2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            cap = std::max(1, std::min(per_sm, 4) * sms);
+        }
+        const int64_t n_items = L.n_chunks * L.n_slabs;
+        const int g = (int)std::min<int64_t>(std::min<int64_t>(n_items, cap), kPackMaxCtas);
+        int32_t a_ncols = n_cols, a_d = d, a_ng = (int32_t)grid.y, a_ns = (int32_t)L.n_slabs;
+        int64_t a_ldf = ld_full;
+        void *args[] = {&a_ncols, &a_d, &a_ng, &a_ns, &src, (void *)&dinv_col, &gmax4, &blockmax, &xp, &xfull, &a_ldf};
+        H2_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)g), dim3(kPackThreads), args, 0, st));
         H2_LAUNCHED("bm_pack_i8_kernel");
         return H2_OK;
     }
@@ -1533,14 +1151,35 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
                                 const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
     H2_REQUIRE(X && aligned16(X), H2_ERR_INVALID, "h2_bm_pack_x_f32: null / misaligned X");
     const int64_t bounds[2] = {0, n_cols};
-    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s);
+    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, true);
+}
+
+// the same on a buffer whose header is known to be armed (h2_graph_bind_workspace zeroes it once): no memset per round
+extern "C" int h2_bm_pack_x_f32_armed(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx,
+                                      const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
+    H2_REQUIRE(X && aligned16(X), H2_ERR_INVALID, "h2_bm_pack_x_f32: null / misaligned X");
+    const int64_t bounds[2] = {0, n_cols};
+    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, false);
+}
+
+// opt-in shared memory size: set once per kernel instantiation and device, not on every launch
+template <typename K>
+static int bm_smem_once(K kern, size_t smem, bool *done) {
+    int dev = 0;
+    H2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return H2_OK;
 }
 
 template <int DG, int S, bool I8 = false>
 static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cudaStream_t st) {
     constexpr size_t smem = BmCfg<DG, S, I8>::kSmem;
     auto kern = bm_mma_kernel<DG, S, I8>;
-    H2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_done[64] = {};
+    { int rc = bm_smem_once(kern, smem, attr_done); if (rc != H2_OK) return rc; }
     kern<<<sc.n_ctas, bm_threads(I8), smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
     if (sc.n_fix > 0) {
@@ -1564,14 +1203,47 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     const bool i8 = splits_i8(splits);
     H2_REQUIRE(h->bit_order == (i8 ? 1 : 0), H2_ERR_INVALID, "h2_bm_spmm_f32: plan was filled with bit order %d, splits=%d needs %d "
                "(h2_bm_fill_order)", h->bit_order, splits, i8 ? 1 : 0);
-    H2_REQUIRE(!i8 || h->n_cols <= (1 << 17), H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: int8 digits need n_cols <= 2^17 (int32 accumulators: 2^17 terms of at most 64 * 128)");
+    const char *base = (const char *)bm_dev;
+    if (h->n_empty_tiles > 0) {
+        bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, Y + out_col_off, ldy);
+        H2_LAUNCHED("bm_zero_tiles_kernel");
+    }
+    if (pair_applies(splits, d)) {
+        // CTA-pair kernel: split tiles are finished in the kernel (no fix-up launch), any number of columns
+        const int fh = pair_fh(d), ng = pair_groups(d);
+        H2_REQUIRE(ng <= 4, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups of %d (max 4): split the columns", d, ng, 2 * fh);
+        const BmSched &sp = h->sched_pair[sched_index(ng)];
+        H2_REQUIRE(sp.n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
+                   H2_ERR_WORKSPACE, "h2_bm_spmm_f32: partial workspace too small");
+        if (sp.n_ctas == 0) return H2_OK;
+        BmPairParams pp;
+        pp.unit_chunk = (const int32_t *)(base + h->off_unit_chunk);
+        pp.bits = (const unsigned long long *)(base + h->off_bits);
+        pp.seg = (const BmPairSeg *)(base + sp.off_seg);
+        pp.cta_seg_ptr = (const int32_t *)(base + sp.off_cta_seg_ptr);
+        pp.xpack = (const uint8_t *)xpack + kI8HeaderBytes;
+        pp.xstep = (const float *)xpack;
+        pp.dinv_row = dinv_row;
+        pp.Y = Y + out_col_off;
+        pp.partial = (float *)partial_ws;
+        pp.sync = (uint32_t *)(const_cast<char *>(base) + sp.off_fix);        // the plan buffer holds the arrival counters
+        {
+            const int64_t nt_ = h->n_tiles;
+            const size_t max_segs = (size_t)(kNumSms / 2 + ng * (nt_ + 1) + ng * (h->n_units / kPairMaxSegUnitsHost + 1) + 2);
+            pp.fix = (const BmPairFix *)(base + sp.off_fix + align_up_sz(max_segs * 8, 256));
+        }
+        pp.n_fix = sp.n_fix;
+        pp.status = (int32_t *)(const_cast<char *>(base) + h->off_status);
+        pp.ldy = ldy;
+        pp.n_rows = h->n_rows; pp.d = d; pp.n_groups_fh = std::max(2, groups_for(d, fh));
+        return pair_launch(splits_pieces(splits), fh, sp.n_ctas, pp, st);
+    }
     const int dg = dg_for(d, splits);
     const int n_groups = groups_for(d, dg);
     H2_REQUIRE(n_groups <= 8, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups (max 8): split the columns", d, n_groups);
     const BmSched &sc = h->sched[sched_index(n_groups)];
     H2_REQUIRE(sc.n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits) && aligned16(partial_ws)),
                H2_ERR_WORKSPACE, "h2_bm_spmm_f32: partial workspace too small");
-    const char *base = (const char *)bm_dev;
     BmParams p;
     p.unit_chunk = (const int32_t *)(base + h->off_unit_chunk);
     p.bits = (const unsigned long long *)(base + h->off_bits);
@@ -1584,28 +1256,7 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
     p.partial = (float *)partial_ws;
     p.ldy = ldy;
     p.n_rows = h->n_rows; p.d = d; p.n_groups = n_groups; p.splits = splits;
-    if (h->n_empty_tiles > 0) {
-        bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, p.Y, ldy);
-        H2_LAUNCHED("bm_zero_tiles_kernel");
-    }
     if (sc.n_ctas == 0) return H2_OK;
-    if (dg == 64 && pair_kernel_applies(splits, n_groups)) {
-        const BmSched &sp = h->sched_pair[sched_index(n_groups / 2)];
-        H2_REQUIRE(sp.n_partial_slots == 0 || (partial_ws && partial_bytes >= h2_bm_partial_bytes(bm_host, d, splits)), H2_ERR_WORKSPACE,
-                   "h2_bm_spmm_f32: partial workspace too small");
-        p.seg = (const BmSegment *)(base + sp.off_seg);
-        p.cta_seg_ptr = (const int32_t *)(base + sp.off_cta_seg_ptr);
-        H2_CUDA(cudaFuncSetAttribute(bm_mma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BmPairCfg::kSmem));
-        bm_mma_pair_kernel<<<2 * sp.n_ctas, kPairThreads, BmPairCfg::kSmem, st>>>(p);   // __cluster_dims__(2, 1, 1)
-        H2_LAUNCHED("bm_mma_pair_kernel");
-        if (sp.n_fix > 0) {
-            bm_fixup_kernel<128><<<dim3((kTileRows * 128 / 4 + 255) / 256, sp.n_fix), 256, 0, st>>>((const BmFix *)(base + sp.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
-            H2_LAUNCHED("bm_fixup_kernel");
-        }
-        return H2_OK;
-    }
-    if (splits == H2_SPLITS_I8X2) return dg == 32 ? bm_launch<32, 2, true>(sc, base, p, st) : bm_launch<64, 2, true>(sc, base, p, st);
-    if (splits == H2_SPLITS_I8X3) return dg == 32 ? bm_launch<32, 3, true>(sc, base, p, st) : bm_launch<64, 3, true>(sc, base, p, st);
     if (splits == 2) return dg == 32 ? bm_launch<32, 2>(sc, base, p, st) : bm_launch<64, 2>(sc, base, p, st);
     return bm_launch<32, 3>(sc, base, p, st);
 }

@@ -46,12 +46,14 @@ struct h2_graph {
     int bm_idx[H2_MAX_HOPS];
     std::vector<char> bm_host[H2_MAX_HOPS];
     void *bm_dev[H2_MAX_HOPS] = {};
-    void *xpack = nullptr, *partial = nullptr;
+    void *xpack = nullptr, *partial = nullptr;   // scratch of the tensor-core hops: a caller workspace (bound) or owned
     size_t xpack_bytes = 0, partial_bytes = 0;
+    void *ws_owned = nullptr;                    // h2_graph_reserve: the library's own allocation behind xpack / partial
     float *x_dev = nullptr, *y_dev = nullptr;
     bool own_xy = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_done = nullptr;               // end of the previous round on this handle (the scratch is per handle)
 };
 
 static int dev_alloc(h2_graph *g, void **p, size_t bytes) {
@@ -63,13 +65,13 @@ static int dev_alloc(h2_graph *g, void **p, size_t bytes) {
 extern "C" int h2_graph_destroy(h2_graph_t *g) {
     if (!g) return H2_OK;
     for (void *p : g->owned) cudaFree(p);
-    if (g->xpack) cudaFree(g->xpack);
-    if (g->partial) cudaFree(g->partial);
+    if (g->ws_owned) cudaFree(g->ws_owned);
     if (g->x_dev) cudaFree(g->x_dev);
     if (g->y_dev) cudaFree(g->y_dev);
     if (g->side) cudaStreamDestroy(g->side);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_join) cudaEventDestroy(g->ev_join);
+    if (g->ev_done) cudaEventDestroy(g->ev_done);
     delete g;
     return H2_OK;
 }
@@ -111,6 +113,10 @@ static int graph_finish(h2_graph *g, const bool *want_bitmap) {
         cudaFree(iws);
         if (rc) return rc;
     }
+    {
+        cudaError_t e = cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cuda_fail(e, "h2_graph: event");
+    }
     if (g->n_bm && g->n_csr) {
         // The tensor-core hops run on an internal HIGH-priority stream and the CSR hops on the caller's stream: the
         // persistent MMA CTAs (1 per SM) are placed first and the gather CTAs fill the remaining register space.
@@ -124,42 +130,78 @@ static int graph_finish(h2_graph *g, const bool *want_bitmap) {
     return H2_OK;
 }
 
-// (re)allocates the per-width scratch of the tensor-core hops; called with the widest d seen so far
-static int graph_reserve(h2_graph *g, int32_t d) {
-    if (d <= g->d_max) return H2_OK;
-    int rc = H2_OK;
-    if (g->n_bm) {
-        size_t pbytes = 0;
-        for (int k = 0; k < g->n_bm; ++k)
-            pbytes = std::max(pbytes, h2_bm_partial_bytes(g->bm_host[g->bm_idx[k]].data(), d, g->splits));
-        // partial-slot counts differ per column-group count: take the max over all widths <= d that change the schedule
-        for (int dd = 4; dd < d; dd *= 2)
-            for (int k = 0; k < g->n_bm; ++k)
-                pbytes = std::max(pbytes, h2_bm_partial_bytes(g->bm_host[g->bm_idx[k]].data(), dd, g->splits));
-        g->xpack_bytes = h2_bm_xpack_bytes(g->n_cols, d, g->splits);
-        g->partial_bytes = pbytes;
-        H2_CUDA(cudaDeviceSynchronize());   // the old scratch may still be in use
-        if (g->xpack) { cudaFree(g->xpack); g->xpack = nullptr; }
-        if (g->partial) { cudaFree(g->partial); g->partial = nullptr; }
-        H2_CUDA(cudaMalloc(&g->xpack, g->xpack_bytes));
-        H2_CUDA(cudaMalloc(&g->partial, g->partial_bytes ? g->partial_bytes : 16));
+// ---- scratch of the tensor-core hops (packed operand + stream-K partial tiles) ---------------------------------------
+// The round entry points never allocate and never synchronise: the scratch for widths <= d_max is either a caller
+// workspace (h2_graph_workspace_bytes + h2_graph_bind_workspace) or the library's own allocation made by the explicit,
+// synchronising h2_graph_reserve (host-buffer handles reserve at h2_graph_create).
+extern "C" int32_t h2_bm_max_width(int32_t splits);
+extern "C" int h2_bm_pack_x_f32_armed(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx,
+                                      const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s);
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void graph_scratch_sizes(const h2_graph *g, int32_t d, size_t *xpack_bytes, size_t *partial_bytes) {
+    *xpack_bytes = *partial_bytes = 0;
+    if (!g->n_bm || d <= 0) return;
+    const int32_t dw = std::min(d, h2_bm_max_width(g->splits));     // wider rounds are computed in column slices
+    *xpack_bytes = h2_bm_xpack_bytes(g->n_cols, dw, g->splits);
+    size_t pbytes = 0;
+    // partial-slot counts differ per column-group count: take the max over every width that changes the schedule
+    for (int dd = 4; ; dd *= 2) {
+        const int32_t w = std::min(dd, dw);
+        for (int k = 0; k < g->n_bm; ++k) pbytes = std::max(pbytes, h2_bm_partial_bytes(g->bm_host[g->bm_idx[k]].data(), w, g->splits));
+        if (dd >= dw) break;
     }
+    *partial_bytes = pbytes;
+}
+
+extern "C" size_t h2_graph_workspace_bytes(const h2_graph_t *g, int32_t d_max) {
+    if (!g) return 0;
+    size_t xb, pb;
+    graph_scratch_sizes(g, d_max, &xb, &pb);
+    return xb || pb ? align256(xb) + align256(pb) + 256 : 0;
+}
+
+extern "C" int h2_graph_bind_workspace(h2_graph_t *g, int32_t d_max, void *ws, size_t ws_bytes) {
+    H2_REQUIRE(g && d_max >= 4 && d_max % 4 == 0, H2_ERR_INVALID, "h2_graph_bind_workspace: bad argument (d_max=%d)", d_max);
+    const size_t need = h2_graph_workspace_bytes(g, d_max);
+    H2_REQUIRE(!need || (ws && ws_bytes >= need && aligned16(ws)), H2_ERR_WORKSPACE,
+               "h2_graph_bind_workspace: %zu bytes needed for d_max=%d, got %zu", need, d_max, ws_bytes);
+    size_t xb, pb;
+    graph_scratch_sizes(g, d_max, &xb, &pb);
+    char *base = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    if (need && xb) H2_CUDA(cudaMemset(base, 0, 256));   // arms the pack kernel's grid-barrier counters (set-up call: may block)
+    g->xpack = need ? base : nullptr;
+    g->xpack_bytes = xb;
+    g->partial = need ? base + align256(xb) : nullptr;
+    g->partial_bytes = pb;
+    g->d_max = d_max;
+    return H2_OK;
+}
+
+// SYNCHRONISES (the old scratch may still be in use) and allocates: call it outside the hot loop.
+extern "C" int h2_graph_reserve(h2_graph_t *g, int32_t d_max) {
+    H2_REQUIRE(g && d_max >= 4 && d_max % 4 == 0, H2_ERR_INVALID, "h2_graph_reserve: bad argument (d_max=%d)", d_max);
+    if (d_max <= g->d_max && (g->xpack || !g->n_bm) && (!g->own_xy || g->x_dev)) return H2_OK;
+    H2_CUDA(cudaDeviceSynchronize());
+    if (g->ws_owned) { cudaFree(g->ws_owned); g->ws_owned = nullptr; g->xpack = g->partial = nullptr; }
+    const size_t need = h2_graph_workspace_bytes(g, d_max);
+    if (need) H2_CUDA(cudaMalloc(&g->ws_owned, need));
+    int rc = h2_graph_bind_workspace(g, d_max, g->ws_owned, need);
+    if (rc != H2_OK) return rc;
     if (g->own_xy) {
-        H2_CUDA(cudaDeviceSynchronize());
         if (g->x_dev) { cudaFree(g->x_dev); g->x_dev = nullptr; }
         if (g->y_dev) { cudaFree(g->y_dev); g->y_dev = nullptr; }
-        H2_CUDA(cudaMalloc((void **)&g->x_dev, (size_t)g->n_cols * d * 4 + 16));
-        H2_CUDA(cudaMalloc((void **)&g->y_dev, (size_t)g->n_rows * g->n_hops * d * 4 + 16));
+        H2_CUDA(cudaMalloc((void **)&g->x_dev, (size_t)g->n_cols * d_max * 4 + 16));
+        H2_CUDA(cudaMalloc((void **)&g->y_dev, (size_t)g->n_rows * g->n_hops * d_max * 4 + 16));
     }
-    g->d_max = d;
-    return rc;
+    return H2_OK;
 }
+static int graph_reserve(h2_graph *g, int32_t d) { return h2_graph_reserve(g, d); }
 
 static bool splits_ok(int32_t s) { return s == 2 || s == 3 || s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
 static bool splits_is_i8(int32_t s) { return s == H2_SPLITS_I8X2 || s == H2_SPLITS_I8X3; }
 
 static bool pick_bitmap(int32_t mode, int32_t splits, bool has_dinv, int64_t nnz, int32_t n_rows, int32_t n_cols) {
-    if (splits_is_i8(splits) && n_cols > (1 << 17)) return false;   // int32 accumulators: <= 2^17 terms of at most 64 * 128
     const double density = (n_rows && n_cols) ? (double)nnz / ((double)n_rows * n_cols) : 0.0;
     // measured crossover on B200 (d = 128): a 256x64 unit costs ~6.9 ns on the tensor cores, a CSR entry ~41 ps of
     // gather => the bitmap wins above ~170 entries per unit, i.e. ~1 % density
@@ -252,7 +294,7 @@ extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
 namespace h2 {
 int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
                   int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
-                  h2_stream_t s);
+                  h2_stream_t s, bool zero_header);
 int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
                 float *xfull, int64_t ld_full, h2_stream_t s);
 }
@@ -271,9 +313,14 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
                             const RoundParts *parts = nullptr) {
     cudaStream_t st = (cudaStream_t)s;
     H2_REQUIRE(g && (X || parts) && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
-    int rc = graph_reserve(g, d);
-    if (rc != H2_OK) return rc;
+    int rc = H2_OK;
+    H2_REQUIRE(!g->n_bm || (d <= g->d_max && g->xpack), H2_ERR_WORKSPACE,
+               "h2_graph_round: width d=%d exceeds the reserved scratch (d_max=%d): call h2_graph_bind_workspace / "
+               "h2_graph_reserve first (the round entry points do not allocate)", d, g->d_max);
+    // The scratch (packed operand, partial tiles) is per handle: a round on another stream waits for the previous one.
+    H2_CUDA(cudaStreamWaitEvent(st, g->ev_done, 0));
     const bool two = g->n_csr && g->n_bm;
+    const int32_t max_w = g->n_bm ? h2_bm_max_width(g->splits) : d;   // widest column slice one tensor-core launch covers
     int first_bm = 0;
     if (parts) {
         // Row-sharded input: the all-gather is fused into the first consumer.  With tensor-core hops the pack kernel
@@ -281,10 +328,11 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
         // the fork so that both streams see its output.  Without tensor-core hops a plain gather kernel does it.
         H2_REQUIRE(!x_offsets, H2_ERR_INVALID, "h2_graph_round: row shards and per-hop input offsets cannot be combined");
         H2_REQUIRE(!g->n_csr || parts->xfull, H2_ERR_INVALID, "h2_graph_round_parts: CSR hops need the x_full scratch");
-        if (g->n_bm) {
+        H2_REQUIRE(!(g->n_bm > 1 || d > max_w) || parts->xfull, H2_ERR_INVALID, "h2_graph_round_parts: several tensor hops / column slices need x_full");
+        if (g->n_bm && d <= max_w) {
             const int h = g->bm_idx[0];
             rc = bm_pack_parts(g->n_cols, d, g->splits, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, g->dinv[h],
-                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s);
+                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s, false);
             if (rc != H2_OK) return rc;
             first_bm = 1;
         } else {
@@ -292,7 +340,6 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
                              parts->ld_full, s);
             if (rc != H2_OK) return rc;
         }
-        H2_REQUIRE(!(g->n_bm > 1) || parts->xfull, H2_ERR_INVALID, "h2_graph_round_parts: several tensor hops need x_full");
         X = parts->xfull;
         ldx = parts->ld_full;
     }
@@ -304,14 +351,18 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
     }
     for (int k = 0; k < g->n_bm; ++k) {
         const int h = g->bm_idx[k];
-        if (!(k == 0 && first_bm)) {
-            rc = h2_bm_pack_x_f32(g->n_cols, d, g->splits, X + (x_offsets ? x_offsets[h] : 0), ldx, g->dinv[h], g->xpack,
-                                  g->xpack_bytes, (h2_stream_t)bm_stream);
+        // rounds wider than one launch covers (8 column groups) are computed in column slices of the same buffers
+        for (int32_t c0 = 0; c0 < d; c0 += max_w) {
+            const int32_t w = std::min(max_w, d - c0);
+            if (!(k == 0 && first_bm)) {
+                rc = h2_bm_pack_x_f32_armed(g->n_cols, w, g->splits, X + (x_offsets ? x_offsets[h] : 0) + c0, ldx, g->dinv[h], g->xpack,
+                                      g->xpack_bytes, (h2_stream_t)bm_stream);
+                if (rc != H2_OK) return rc;
+            }
+            rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], w, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
+                                offsets[h] + c0, g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
             if (rc != H2_OK) return rc;
         }
-        rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], d, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
-                            offsets[h], g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
-        if (rc != H2_OK) return rc;
     }
     if (g->n_csr) {
         h2_hop_t sub[H2_MAX_HOPS];
@@ -339,6 +390,7 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
             H2_CUDA(cudaMemcpy2DAsync(y_host + off, (size_t)ldy * 4, Y + off, (size_t)ldy * 4, (size_t)d * 4,
                                       (size_t)g->n_rows, cudaMemcpyDeviceToHost, st));
         }
+    H2_CUDA(cudaEventRecord(g->ev_done, st));
     return H2_OK;
 }
 
@@ -367,7 +419,8 @@ extern "C" int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host
     cudaStream_t st = (cudaStream_t)s;
     H2_REQUIRE(g && x_host && y_host && d >= 4 && d % 4 == 0 && g->own_xy, H2_ERR_INVALID,
                "h2_graph_round_host: bad argument (d=%d) or handle created over device arrays", d);
-    { int rc0 = graph_reserve(g, d); if (rc0 != H2_OK) return rc0; }
+    H2_REQUIRE(d <= g->d_max, H2_ERR_WORKSPACE, "h2_graph_round_host: d=%d exceeds the d_max=%d the handle was created with "
+               "(h2_graph_reserve)", d, g->d_max);
     int64_t offsets[H2_MAX_HOPS];
     for (int h = 0; h < g->n_hops; ++h) offsets[h] = (int64_t)h * d;  // GCNLayer + Flatten layout: [N, H*d]
     const int64_t ldy = (int64_t)g->n_hops * d;

@@ -246,7 +246,9 @@ static int launch_gather(const RoundParams &p, cudaStream_t st) {
     const int64_t grid = p.n_cta_rows + (warp_rows + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid == 0) return H2_OK;
     H2_REQUIRE(grid < 0x7fffffffLL, H2_ERR_UNSUPPORTED, "fused round: grid of %lld CTAs exceeds 2^31", (long long)grid);
-    const size_t smem = (size_t)kWarpsPerCta * p.d4 * sizeof(float4);
+    // the partial rows are only needed by CTA-rows; without them the CTA takes no shared memory and fits next to the
+    // persistent tensor-core CTA of the same round
+    const size_t smem = p.n_cta_rows ? (size_t)kWarpsPerCta * p.d4 * sizeof(float4) : 0;
     fused_hops_gather_kernel<LPR, NV><<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
     H2_LAUNCHED("fused_hops_gather_kernel");
     return H2_OK;

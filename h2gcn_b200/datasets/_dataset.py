@@ -231,7 +231,14 @@ class GraphData:
             raise NotImplementedError("dense adjacency tensors are not part of the H2GCN path (SURVEY.md §2 #4)")
         tensors.adj = tensors.sparse_adj
         if getAdjHops:
-            raise NotImplementedError("getAdjHops (dense un-normalised hop stack) is only used by models without G layers")
+            # _dataset.py:551-558: un-normalised merged hop patterns.  The reference densifies them into one
+            # [N, H, N] constant; the only models that ask for them (setups without a G layer: the MLP configs
+            # M64-R-MO, M64-D-MO, ...) never read the tensor, so they stay sparse device tensors here (same hops,
+            # same order, values 1.0) instead of an O(N^2) array.
+            hops = [[int(x) for x in str(elem).split(",")] for elem in getAdjHops]
+            splits = TransformSPAdj.nhoodSplit(tensors.adj, max(chain(*hops)))
+            n = self.num_samples
+            tensors.adj_hops = [splits[e[0]] if len(e) == 1 else _merge_patterns([splits[i] for i in e], n, n) for e in hops]
         if getAdjNormHops:
             hops = [[int(x) for x in str(elem).split(",")] for elem in getAdjNormHops]
             hop_max = max(chain(*hops))

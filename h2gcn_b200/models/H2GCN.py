@@ -109,6 +109,7 @@ class _FusedProgram:
 
     def __init__(self, model, adjhops, feat_dim, n_rows, device):
         self.ok = False
+        self.dropout_feeds_classifier = []   # one flag per Dropout layer met by the symbolic execution
         objs = model.layer_objs
         leaves = {}      # leaf id -> dict(width, kind, ...)
         cur = None       # list of leaf ids (symbolic current tensor); None = the sparse input
@@ -141,8 +142,12 @@ class _FusedProgram:
                 cur = [lid]
                 if ind + 1 >= len(objs) or not isinstance(objs[ind + 1], layers.Flatten):
                     return  # a 3-D [N,H,d] tensor flows on: interpreter only
-            elif isinstance(layer, (layers.Flatten, layers.Dropout)):
+            elif isinstance(layer, layers.Flatten):
                 pass
+            elif isinstance(layer, layers.Dropout):
+                # inference: identity.  Training applies ONE dropout, on the classifier input: remember where the
+                # Dropout layers sit so that loss_and_grads can refuse any other placement instead of ignoring it.
+                self.dropout_feeds_classifier.append(ind + 1 == len(objs) - 1 and isinstance(objs[-1], layers.Dense))
             elif isinstance(layer, layers.ConcatLayer):
                 sel = [v for name, v in tagged.items() if name in layer.tags]
                 cur = (list(cur) if layer.addInputs else []) + [l for v in sel for l in v]
@@ -391,6 +396,11 @@ class H2GCN:
             raise NotImplementedError("training is implemented for the fused layer-list family only")
         if any(getattr(l, "use_bias", False) for l in self.layer_objs):
             raise NotImplementedError("training with bias terms (F layers) is not wired up")
+        if not all(prog.dropout_feeds_classifier):
+            # e.g. M64-R-D0.5-T1-G-V-...: keras would drop activations in the middle of the network; the fused
+            # training path only implements the H2GCN placement (Dropout directly in front of the final Dense)
+            raise NotImplementedError("training: a Dropout layer that does not directly feed the final Dense layer is "
+                                      "not implemented on the fused path")
         if dropout_rate is None:
             rates = [l.rate for l in self.layer_objs if isinstance(l, layers.Dropout)]
             dropout_rate = rates[-1] if rates else 0.0

@@ -146,18 +146,17 @@ class GCNLayer(_Named):
     def selected(self, adjhops):
         return [x for ind, x in enumerate(adjhops) if (self.hops is None or ind in self.hops)]
 
-    # plans are shared by every GCNLayer that aggregates over the same hop tensors (both rounds of H2GCN-2): the
-    # schedule and the tile-bitmap format are built once per graph.  Entries keep the hop tensors alive, so ids stay valid.
-    _shared_plans = {}
-
+    # The plan (schedule, tile-bitmap format, scratch) is built once per graph and shared by every GCNLayer that
+    # aggregates over the same hop tensors (both rounds of H2GCN-2).  It is stored ON the first hop tensor, so it lives
+    # exactly as long as the graph's tensors do (no process-global cache pinning device memory), and the handle
+    # serialises rounds issued from different streams (include/h2gcn_b200.h, h2_graph_bind_workspace).
     def plan_for(self, adjhops):
         sel = self.selected(adjhops)
+        cache = sel[0].__dict__.setdefault("_hop_plans", {})
         key = tuple(id(x) for x in sel)
-        entry = GCNLayer._shared_plans.get(key)
+        entry = cache.get(key)
         if entry is None:
-            if len(GCNLayer._shared_plans) >= 16:          # small LRU-less bound: drop the oldest graph
-                GCNLayer._shared_plans.pop(next(iter(GCNLayer._shared_plans)))
-            entry = GCNLayer._shared_plans[key] = (sel, ops.HopPlan(sel))
+            entry = cache[key] = (sel[1:], ops.HopPlan(sel))     # keeps the other hop tensors alive: ids stay valid
         return entry[1]
 
     def sparse_dense_matmul(self, sp_a, b, ind=""):

@@ -210,6 +210,7 @@ class HopPlan:
         with torch.cuda.device(hops[0].device):
             check(lib().h2_graph_create_device(self.n_rows, self.n_cols, H, desc, nnz, hops[0].row_begin, self.MODES[mode],
                                                splits, ctypes.byref(self._h)))
+        self._ws, self._ws_d = [], 0      # caller-owned scratch of the tensor-core hops (torch allocations, bound below)
         fmt = (ctypes.c_int32 * H)()
         check(lib().h2_graph_formats(self._h, fmt))
         self.tensor_idx = [k for k in range(H) if fmt[k] == 1]
@@ -217,6 +218,19 @@ class HopPlan:
         self.kernel_name = " + ".join(
             (["bm_mma_kernel (tcgen05 tile-bitmap, %s) x%d" % (_cabi.SPLITS_NAME[splits], len(self.tensor_idx))] if self.tensor_idx else []) +
             (["fused_hops_gather_kernel (CSR gather) over %d hop(s)" % len(self.csr_idx)] if self.csr_idx else []))
+
+    def reserve(self, d):
+        """Scratch for rounds of width <= d: allocated here by the CALLER (torch's allocator) and bound to the handle
+        (h2_graph_workspace_bytes / h2_graph_bind_workspace) — the round entry points never allocate or synchronise.
+        Earlier, narrower workspaces stay alive until the plan is closed (rounds using them may still be in flight)."""
+        if d <= self._ws_d:
+            return
+        d = (d + 3) // 4 * 4
+        nbytes = int(lib().h2_graph_workspace_bytes(self._h, d))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.hops[0].device)
+        check(lib().h2_graph_bind_workspace(self._h, d, ptr(ws), nbytes))
+        self._ws.append(ws)
+        self._ws_d = d
 
     def run(self, x, out, offsets, d=None, stream=None):
         """out[:, offsets[h] : offsets[h]+d] = hops[h] @ x[:, :d]   (x, out may be column slices of one buffer)."""
@@ -236,6 +250,7 @@ class HopPlan:
             raise ValueError(f"fused round: d={d}, leading dimensions and column offsets must be multiples of 4 "
                              "and the buffers 16-byte aligned")
         offs = (ctypes.c_int64 * len(offsets))(*offsets)
+        self.reserve(d)
         check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(out), out.stride(0), offs, stream_ptr(stream)))
         return out
 
@@ -251,6 +266,7 @@ class HopPlan:
             raise ValueError("shape mismatch / one offset per hop")
         xo = (ctypes.c_int64 * len(x_offsets))(*x_offsets)
         yo = (ctypes.c_int64 * len(offsets))(*offsets)
+        self.reserve(d)
         check(lib().h2_graph_round_multi(self._h, d, ptr(x), x.stride(0), xo, ptr(out), out.stride(0), yo, stream_ptr(stream)))
         return out
 
@@ -263,6 +279,7 @@ class HopPlan:
         ptrs = (ctypes.c_void_p * P)(*part_ptrs)
         bnd = (ctypes.c_int64 * (P + 1))(*[int(b) for b in bounds])
         yo = (ctypes.c_int64 * len(offsets))(*offsets)
+        self.reserve(d)
         check(lib().h2_graph_round_parts(self._h, d, P, ptrs, bnd, ld_part, ptr(x_full), x_full.stride(0), ptr(out),
                                          out.stride(0), yo, stream_ptr(stream)))
         return out
@@ -271,6 +288,7 @@ class HopPlan:
         if getattr(self, "_h", None):
             lib().h2_graph_destroy(self._h)
             self._h = ctypes.c_void_p()
+            self._ws = []
 
     def __del__(self):
         try:

@@ -43,6 +43,7 @@ enum {
 #define H2_MAX_HOPS 8
 
 typedef void *h2_stream_t; /* cudaStream_t */
+typedef struct h2_graph h2_graph_t;
 
 /* One normalised hop adjacency \bar{A}_h as the reference hands it to GCNLayer (a tf.SparseTensor, row-major sorted;
  * h2gcn/datasets/_dataset.py:528-535), in CSR form, plus where its product lands in the output row:
@@ -157,7 +158,12 @@ int h2_bm_fill(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int3
 /* same with an explicit bitmap bit order: 0 = natural (bf16 `splits`), 1 = int8 `splits` */
 int h2_bm_fill_order(int32_t n_rows, int32_t n_cols, const int64_t *rowptr, const int32_t *col, void *index_ws,
                      int64_t n_units, void *bm_host, void *bm_dev, size_t bm_dev_bytes, int32_t bit_order, h2_stream_t s);
-/* per round: pack X' once per distinct dinv_col (NULL = no column scaling), then one h2_bm_spmm_f32 per hop. */
+/* widest d one pack + spmm pair covers (8 column groups: 512 for the int8 digits and 2 bf16 pieces, 256 for 3 bf16
+ * pieces); the h2_graph_round* entry points compute wider rounds in column slices of the same buffers. */
+int32_t h2_bm_max_width(int32_t splits);
+/* per round: pack X' once per distinct dinv_col (NULL = no column scaling), then one h2_bm_spmm_f32 per hop.
+ * Non-finite inputs: the int8 operand has ONE step for the whole matrix, so NaN is packed as 0 and +-Inf saturates to the
+ * largest finite magnitude instead of poisoning every output (the fp32 CSR path propagates them like the reference). */
 size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits);
 size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits);
 int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx, const float *dinv_col,
@@ -186,7 +192,6 @@ int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int64_t ldx, fl
  * dinv_host[h]: fp32 [n_cols] scale vector when hop h is a normalised BINARY pattern (val = dinv[i]*dinv[j]); it
  * enables the tensor-core format for that hop (NULL entry / NULL array: CSR only).  row_begin: global index of local
  * row 0.  mode: 0 = auto (bitmap for density >= 1 %), 1 = CSR everywhere, 2 = bitmap wherever dinv is given. */
-typedef struct h2_graph h2_graph_t;
 int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_t *const *rowptr_host,
                     const int32_t *const *col_host, const float *const *val_host, const float *const *dinv_host,
                     int32_t row_begin, int32_t d_max, int32_t mode, int32_t splits, h2_graph_t **out);
@@ -195,6 +200,16 @@ int h2_graph_create(int32_t n_rows, int32_t n_cols, int32_t n_hops, const int64_
  * is given (factored CSR); hops with dinv may take the tensor-core format.  nnz_host[h] = stored entries of hop h. */
 int h2_graph_create_device(int32_t n_rows, int32_t n_cols, int32_t n_hops, const h2_hop_t *hops, const int64_t *nnz_host,
                            int32_t row_begin, int32_t mode, int32_t splits, h2_graph_t **out);
+/* Scratch of the tensor-core hops (packed operand, stream-K partial tiles) for rounds of width <= d_max.  The round entry
+ * points below NEVER allocate or synchronise: before the first round either bind a caller-owned workspace of
+ * h2_graph_workspace_bytes(g, d_max) bytes (16-byte aligned, alive while rounds are in flight), or let the library
+ * allocate with h2_graph_reserve (SYNCHRONISES; h2_graph_create does this for its d_max).  A round wider than the reserved
+ * d_max returns H2_ERR_WORKSPACE.  The scratch is per handle: rounds on the same handle are serialised by an event the
+ * handle records at the end of every round (a round issued on another stream waits for the previous one), so a handle
+ * may be used from several streams; independent rounds that should OVERLAP need one handle each. */
+size_t h2_graph_workspace_bytes(const h2_graph_t *g, int32_t d_max);
+int h2_graph_bind_workspace(h2_graph_t *g, int32_t d_max, void *ws, size_t ws_bytes);
+int h2_graph_reserve(h2_graph_t *g, int32_t d_max);
 /* fmt_out[h] = 0 (CSR) / 1 (tile bitmap, tensor cores) */
 int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out);
 int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_host, h2_stream_t s);
