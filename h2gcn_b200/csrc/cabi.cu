@@ -318,7 +318,12 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
                "h2_graph_round: width d=%d exceeds the reserved scratch (d_max=%d): call h2_graph_bind_workspace / "
                "h2_graph_reserve first (the round entry points do not allocate)", d, g->d_max);
     // The scratch (packed operand, partial tiles) is per handle: a round on another stream waits for the previous one.
-    H2_CUDA(cudaStreamWaitEvent(st, g->ev_done, 0));
+    // (Not while the stream is being captured into a CUDA graph: a graph is ordered by construction and may not wait on
+    // an event recorded outside the capture.)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    H2_CUDA(cudaStreamIsCapturing(st, &cap));
+    const bool guard = cap == cudaStreamCaptureStatusNone;
+    if (guard) H2_CUDA(cudaStreamWaitEvent(st, g->ev_done, 0));
     const bool two = g->n_csr && g->n_bm;
     const int32_t max_w = g->n_bm ? h2_bm_max_width(g->splits) : d;   // widest column slice one tensor-core launch covers
     int first_bm = 0;
@@ -390,7 +395,7 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
             H2_CUDA(cudaMemcpy2DAsync(y_host + off, (size_t)ldy * 4, Y + off, (size_t)ldy * 4, (size_t)d * 4,
                                       (size_t)g->n_rows, cudaMemcpyDeviceToHost, st));
         }
-    H2_CUDA(cudaEventRecord(g->ev_done, st));
+    if (guard) H2_CUDA(cudaEventRecord(g->ev_done, st));
     return H2_OK;
 }
 

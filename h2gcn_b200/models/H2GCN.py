@@ -225,6 +225,25 @@ class _FusedProgram:
                 gW0 = ops.sparse_dense(features_t, g0.contiguous())        # X^T . dr0  ->  [F, p]
         return gW0, gW_out
 
+    def capture(self, features):
+        """The whole launch sequence of `run` as ONE CUDA graph: on Cora-sized graphs the forward is a
+        handful of ~5-30 us kernels and the Python / launch overhead between them is a large part of the wall time.
+        Returns the torch.cuda.CUDAGraph; `graph_out` holds the logits it writes.  The graph reads the SAME feature tensor,
+        weights and concat buffer: replay after updating them in place."""
+        for lid in self.steps:     # scratch must be bound before the capture (no allocation inside)
+            lf = self.leaves[lid]
+            if lf["kind"] == "gcn":
+                lf["layer"].plan_for(self.adjhops).reserve(lf["d"])
+        side = torch.cuda.Stream(device=self.buf.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.run(features)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            self.graph_out = self.run(features)
+        return graph
+
     def run(self, features, classify=True):
         buf = self.buf
         for lid in self.steps:

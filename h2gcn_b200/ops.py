@@ -130,16 +130,16 @@ def hop2_pattern(rowptr, col, row_begin=0, row_end=None, stream=None):
     return rp2, col2
 
 
-def sym_normalize(rowptr, col, n_cols=None, row_begin=0, deg_all=None, stream=None):
+def sym_normalize(rowptr, col, n_cols=None, row_begin=0, deg_all=None, stream=None, want_val=True):
     """normalize(., SYM_NORMALIZED) (_dataset.py:114-118) for a binary pattern.
-    Returns (val fp32 [nnz], dinv64 [n_cols], dinv32 [n_cols])."""
+    Returns (val fp32 [nnz] or None when want_val is False, dinv64 [n_cols], dinv32 [n_cols])."""
     require_cuda(rowptr, col)
     n_rows = rowptr.numel() - 1
     n_cols = n_rows if n_cols is None else n_cols
     dev = rowptr.device
     rowptr = _i64(rowptr).contiguous()
     col = col.to(torch.int32).contiguous()
-    val = torch.empty(col.numel(), dtype=torch.float32, device=dev)
+    val = torch.empty(col.numel(), dtype=torch.float32, device=dev) if want_val else None
     d64 = torch.empty(n_cols, dtype=torch.float64, device=dev)
     d32 = torch.empty(n_cols, dtype=torch.float32, device=dev)
     check(lib().h2_sym_normalize(n_rows, n_cols, row_begin, ptr(rowptr), ptr(col), ptr(deg_all), ptr(d64), ptr(d32),

@@ -92,9 +92,17 @@ class ShardedGraph:
     equal-rows split and all-gathered (they are also the global degree vector D2 the normalisation needs), the
     nnz-balanced boundaries are derived from them, then every rank fills and normalises its own rows."""
 
-    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=None, exchange="auto"):
+    def __init__(self, adj_scipy, rank, world, device, factored=False, group=None, mode="auto", splits=None, exchange="auto",
+                 explicit_vals=True, balance="auto"):
+        """explicit_vals=False: the fp32 values of the hop adjacencies are never materialised (factored CSR: the kernels
+        rebuild dinv_i * dinv_j; implies factored=True) — BASELINE config 4's 2-hop ring has ~2e10 entries.
+        balance: how the contiguous row ranges are cut — "nnz" (stored entries of [A1; A2]: what the CSR gather costs),
+        "rows" (equal row counts: what the tile-bitmap path costs, whose work is rows x columns whatever the entries),
+        "auto" = "rows" when the 2-hop pattern is dense enough for the tensor-core format, else "nnz"."""
         from . import ops
         self.rank, self.world, self.device, self.group = rank, world, device, group
+        if not explicit_vals:
+            factored = True
         a = adj_scipy.tocsr()
         a.sort_indices()
         n = a.shape[0]
@@ -109,8 +117,19 @@ class ShardedGraph:
         cnt = torch.empty(hi - lo, dtype=torch.int64, device=device)
         ops.check(ops.lib().h2_hop2_count(n, ops.ptr(rp), ops.ptr(col), lo, hi, ops.ptr(cnt), ops.stream_ptr()))
         deg2 = all_gather_counts(cnt, eq, group)
-        # nnz-balanced contiguous partition over the stacked rows
-        self.bounds = partition_rows((deg1 + deg2).cpu().numpy(), world)
+        self.deg2_host = deg2.cpu().numpy()
+        d1 = deg1.cpu().numpy()
+        self.max_deg1, self.max_deg2 = int(d1.max(initial=0)), int(self.deg2_host.max(initial=0))
+        self.zero_deg1, self.zero_deg2 = int((d1 == 0).sum()), int((self.deg2_host == 0).sum())
+        # contiguous row partition
+        if balance == "auto":
+            dens2 = float(self.deg2_host.sum()) / max(1.0, float(n) * n)
+            balance = "rows" if (mode != "csr" and dens2 >= 0.01) else "nnz"
+        if balance == "rows":
+            self.bounds = eq.copy()
+        else:
+            self.bounds = partition_rows((deg1 + deg2).cpu().numpy(), world)
+        self.balance = balance
         self.row_begin, self.row_end = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.n_local = self.row_end - self.row_begin
         b, e = self.row_begin, self.row_end
@@ -120,10 +139,10 @@ class ShardedGraph:
         ops.check(ops.lib().h2_hop2_fill(n, ops.ptr(rp), ops.ptr(col), b, e, ops.ptr(rp2), ops.ptr(col2), ops.stream_ptr()))
         rp1 = (rp[b:e + 1] - rp[b]).contiguous()
         col1 = col[int(rp[b].item()):int(rp[e].item())].contiguous()
-        v1, _, d1 = ops.sym_normalize(rp1, col1, n_cols=n, row_begin=b, deg_all=deg1.contiguous())
-        v2, _, d2 = ops.sym_normalize(rp2, col2, n_cols=n, row_begin=b, deg_all=deg2.contiguous())
-        self.hops = [ops.SparseTensor(rp1, col1, v1, (self.n_local, n), row_begin=b, dinv=d1),
-                     ops.SparseTensor(rp2, col2, v2, (self.n_local, n), row_begin=b, dinv=d2)]
+        v1, _, d1v = ops.sym_normalize(rp1, col1, n_cols=n, row_begin=b, deg_all=deg1.contiguous(), want_val=explicit_vals)
+        v2, _, d2v = ops.sym_normalize(rp2, col2, n_cols=n, row_begin=b, deg_all=deg2.contiguous(), want_val=explicit_vals)
+        self.hops = [ops.SparseTensor(rp1, col1, v1, (self.n_local, n), row_begin=b, dinv=d1v),
+                     ops.SparseTensor(rp2, col2, v2, (self.n_local, n), row_begin=b, dinv=d2v)]
         self.plan = ops.HopPlan(self.hops, factored=factored, mode=mode, splits=splits)
         self.nnz2_local = int(col2.numel())
         self.nnz_local = int(col1.numel()) + self.nnz2_local

@@ -85,19 +85,19 @@ def test_splits_codes():
 @pytest.mark.parametrize("pieces,rng_bound", [(2, 32639), (3, 8355711)])
 def test_int8_operand_model(pieces, rng_bound):
     """tests/util.py: i8_block_quantize is the model the GPU test compares the int8 kernel with EXACTLY: its own
-    invariants — digits range, block exponents 0..6 relative to the global maximum, error bound per element."""
+    invariants — digits range, ROW exponents 0..6 relative to the global maximum, error bound per element."""
     from tests import util
     rng = np.random.default_rng(pieces)
     x = (rng.standard_normal((403, 24)) * np.exp(rng.uniform(-12, 0, size=(403, 1)))).astype(np.float32)
     x[100:104] = 0.0
     deq, step, t = util.i8_block_quantize(x, pieces)
-    assert t.min() >= 0 and t.max() <= 6 and len(t) == 101 and t[25] == 0           # 403 rows -> 101 groups of 4
-    g = int(np.argmax(np.abs(x).max(axis=1))) // 4
-    assert t[g] == 6, "the group holding the global maximum gets the largest block exponent"
-    q = deq / (step * np.ldexp(1.0, np.repeat(t, 4)[:403])[:, None])
+    assert t.min() >= 0 and t.max() <= 6 and len(t) == 403 and (t[100:104] == 0).all()     # one exponent per row
+    g = int(np.argmax(np.abs(x).max(axis=1)))
+    assert t[g] == 6, "the row holding the global maximum gets the largest exponent"
+    q = deq / (step * np.ldexp(1.0, t)[:, None])
     assert np.allclose(q, np.rint(q)) and np.abs(q).max() <= rng_bound
-    # |error| <= half a step of the element's group (+ the fp32 rounding of the scaled value)
-    bound = 0.5 * step * np.ldexp(1.0, np.repeat(t, 4)[:403])[:, None] * (1 + 1e-6) + np.abs(x) * 2.0 ** -23
+    # |error| <= half a step of the element's row (+ the fp32 rounding of the scaled value)
+    bound = 0.5 * step * np.ldexp(1.0, t)[:, None] * (1 + 1e-6) + np.abs(x) * 2.0 ** -23
     assert (np.abs(deq - x) <= bound).all()
     # balanced base-256 digits reproduce q
     qi = np.rint(q).astype(np.int64)
