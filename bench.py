@@ -671,6 +671,8 @@ def main_multi(args):
     def step(k=0):
         g.round(x_local, y, [0, d])
 
+    torch.cuda.synchronize()
+    dist.barrier()                 # the set-up times differ by seconds between ranks (rank 0 owns the hub rows)
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()

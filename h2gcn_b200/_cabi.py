@@ -16,6 +16,7 @@ c_i32, c_i64, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctyp
 
 # `splits` codes of the tensor-core path (include/h2gcn_b200.h): 2 / 3 bf16 pieces, or int8 digits
 H2_SPLITS_I8X2, H2_SPLITS_I8X3 = 18, 19
+H2_F32, H2_BF16 = 0, 1     # element type codes of the feature matrices of a round
 SPLITS = {2: 2, 3: 3, "bf16x2": 2, "bf16x3": 3, "i8x2": H2_SPLITS_I8X2, "i8x3": H2_SPLITS_I8X3,
           H2_SPLITS_I8X2: H2_SPLITS_I8X2, H2_SPLITS_I8X3: H2_SPLITS_I8X3}
 SPLITS_NAME = {2: "2 bf16 pieces", 3: "3 bf16 pieces", H2_SPLITS_I8X2: "2 int8 digits + block exponents",
@@ -68,6 +69,8 @@ PROTOTYPES = {
     "h2_plan_build": (ctypes.c_int, [c_i32, c_i32, ctypes.POINTER(HopDesc), c_vp, c_vp, c_vp, c_sz, c_vp]),
     "h2_fused_hops_spmm_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(HopDesc), c_i32, c_vp, c_i64,
                                               c_vp, c_i64, c_vp]),
+    "h2_fused_hops_spmm_ex": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(HopDesc), c_i32, c_vp, c_i64, c_i32,
+                                             c_vp, c_i64, c_i32, c_vp]),
     "h2_bm_host_bytes": (c_sz, []),
     "h2_bm_index_bytes": (c_sz, [c_i32, c_i32]),
     "h2_bm_count": (ctypes.c_int, [c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, ctypes.POINTER(c_i64), c_vp]),
@@ -78,9 +81,11 @@ PROTOTYPES = {
     "h2_bm_xpack_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "h2_bm_partial_bytes": (c_sz, [c_vp, c_i32, c_i32]),
     "h2_bm_pack_x_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "h2_bm_pack_x_f32_armed": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "h2_bm_spmm_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "h2_sparse_dense_f32": (ctypes.c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
     "h2_dense_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
+    "h2_dense_tc_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
     "h2_relu_slice_f32": (ctypes.c_int, [c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),
     "h2_graph_create": (ctypes.c_int, [c_i32, c_i32, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                                        ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_i32, c_i32, c_i32, c_i32,
@@ -93,6 +98,7 @@ PROTOTYPES = {
     "h2_graph_formats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32)]),
     "h2_graph_round_host": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "h2_graph_round": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "h2_graph_round_ex": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "h2_graph_round_multi": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "h2_graph_round_parts": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i64, c_vp, c_i64,
                                             c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),

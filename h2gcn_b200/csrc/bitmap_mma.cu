@@ -90,7 +90,7 @@ struct PackSrc {
     const float *ptr[8];
     int32_t bound[9];
     int32_t n_parts;
-    int32_t pad;
+    int32_t bf16;      // rows hold bf16 (ld counts bf16 elements); int8 pack only, single part
     int64_t ld;
 };
 
@@ -98,7 +98,15 @@ __device__ __forceinline__ const float *pack_src_row(const PackSrc &src, int j) 
     int q = 0;
 #pragma unroll
     for (int t = 1; t < 8; ++t) q += (t < src.n_parts && j >= src.bound[t]) ? 1 : 0;
+    if (src.bf16) return reinterpret_cast<const float *>(reinterpret_cast<const uint16_t *>(src.ptr[q]) + (int64_t)(j - src.bound[q]) * src.ld);
     return src.ptr[q] + (int64_t)(j - src.bound[q]) * src.ld;
+}
+// 4 consecutive features starting at feature f of a source row (fp32: 16 bytes, bf16: 8 bytes widened)
+__device__ __forceinline__ float4 pack_src_load4(const PackSrc &src, const float *row, int f) {
+    if (!src.bf16) return *reinterpret_cast<const float4 *>(row + f);
+    const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(row) + f);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
 }
 
 template <int DG>
@@ -221,9 +229,8 @@ __global__ void __launch_bounds__(kPackThreads) bm_pack_i8_kernel(int32_t n_cols
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             sc[i] = 0.f;
             if (j < n_cols && f0 + f4 < d) {   // d % 4 == 0: a float4 is either fully inside or fully outside
-                const float *p = (first_pass || !xfull) ? pack_src_row(src, j) + f0 + f4      // plain load: may be peer memory
-                                                        : xfull + (int64_t)j * ld_full + f0 + f4;   // second pass: the local copy
-                v[i] = *reinterpret_cast<const float4 *>(p);
+                if (first_pass || !xfull) v[i] = pack_src_load4(src, pack_src_row(src, j), f0 + f4);   // plain load: may be peer memory
+                else v[i] = *reinterpret_cast<const float4 *>(xfull + (int64_t)j * ld_full + f0 + f4);   // second pass: the local copy
                 sc[i] = dinv ? __ldg(dinv + j) : 1.f;
             }
         }
@@ -832,7 +839,7 @@ struct BmPairFix { int32_t tile, group, slot_begin, n_slots; };
 struct BmPairParams {
     const int32_t *unit_chunk; const unsigned long long *bits; const BmPairSeg *seg; const int32_t *cta_seg_ptr;
     const uint8_t *xpack; const float *xstep; const float *dinv_row; float *Y; float *partial; const BmPairFix *fix;
-    uint32_t *sync; int32_t *status; int32_t n_fix; int64_t ldy; int32_t n_rows, d, n_groups_fh;
+    uint32_t *sync; int32_t *status; int32_t n_fix; int64_t ldy; int32_t n_rows, d, n_groups_fh, y_bf16;
 };
 void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int n_pairs_max, std::vector<BmPairSeg> &segs,
                    std::vector<int32_t> &pair_ptr, std::vector<BmPairFix> &fixes, int *n_slots_out);
@@ -1084,15 +1091,18 @@ static int fill_src(PackSrc &src, int32_t n_cols, int32_t n_parts, const float *
 // pack from row shards (n_parts pointers + bounds); xfull != nullptr also writes the gathered fp32 matrix
 int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
                   int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
-                  h2_stream_t s, bool zero_header) {
+                  h2_stream_t s, bool zero_header, bool x_bf16) {
     H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && splits_valid(splits) && xpack && ld >= d && ld % 4 == 0,
                H2_ERR_INVALID, "bm_pack: bad argument (d=%d splits=%d)", d, splits);
+    H2_REQUIRE(!x_bf16 || (splits_i8(splits) && n_parts == 1 && !xfull && d % 8 == 0 && ld % 8 == 0), H2_ERR_UNSUPPORTED,
+               "bm_pack: bf16 rows need the int8 digits, a single part and d, ld multiples of 8");
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
                "bm_pack: xpack buffer too small / misaligned");
     H2_REQUIRE(!xfull || (ld_full >= d && ld_full % 4 == 0 && aligned16(xfull)), H2_ERR_ALIGN, "bm_pack: xfull alignment");
     PackSrc src;
     int rc = fill_src(src, n_cols, n_parts, ptrs, bounds, ld);
     if (rc != H2_OK) return rc;
+    src.bf16 = x_bf16 ? 1 : 0;
     const int dg = dg_for(d, splits);
     dim3 grid((unsigned)((n_cols + kChunkCols - 1) / kChunkCols), (unsigned)groups_for_splits(d, dg, splits));
     cudaStream_t st = (cudaStream_t)s;
@@ -1151,7 +1161,7 @@ extern "C" int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const
                                 const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
     H2_REQUIRE(X && aligned16(X), H2_ERR_INVALID, "h2_bm_pack_x_f32: null / misaligned X");
     const int64_t bounds[2] = {0, n_cols};
-    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, true);
+    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, true, false);
 }
 
 // the same on a buffer whose header is known to be armed (h2_graph_bind_workspace zeroes it once): no memset per round
@@ -1159,7 +1169,7 @@ extern "C" int h2_bm_pack_x_f32_armed(int32_t n_cols, int32_t d, int32_t splits,
                                       const float *dinv_col, void *xpack, size_t xpack_bytes, h2_stream_t s) {
     H2_REQUIRE(X && aligned16(X), H2_ERR_INVALID, "h2_bm_pack_x_f32: null / misaligned X");
     const int64_t bounds[2] = {0, n_cols};
-    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, false);
+    return bm_pack_parts(n_cols, d, splits, 1, &X, bounds, ldx, dinv_col, xpack, xpack_bytes, nullptr, 0, s, false, false);
 }
 
 // opt-in shared memory size: set once per kernel instantiation and device, not on every launch
@@ -1190,9 +1200,29 @@ static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cud
 }
 
 // Y[:, off:off+d] = diag(dinv_row) . P . X'  for the bitmap-format pattern P (X' from h2_bm_pack_x_f32).
+static int bm_spmm_impl(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
+                        const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
+                        size_t partial_bytes, h2_stream_t s, bool y_bf16);
+
 extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
                               const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
                               size_t partial_bytes, h2_stream_t s) {
+    return bm_spmm_impl(bm_host, bm_dev, d, splits, xpack, dinv_row, Y, ldy, out_col_off, partial_ws, partial_bytes, s, false);
+}
+
+namespace h2 {
+// bf16 output rows (ldy / out_col_off count bf16 elements); int8 digits only
+int bm_spmm_bf16_out(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack, const float *dinv_row,
+                     void *Y, int64_t ldy, int64_t out_col_off, void *partial_ws, size_t partial_bytes, h2_stream_t s) {
+    H2_REQUIRE(splits_i8(splits) && d % 8 == 0 && ldy % 8 == 0 && out_col_off % 8 == 0, H2_ERR_UNSUPPORTED,
+               "bf16 output needs the int8 digits and d, ldy, offsets multiples of 8");
+    return bm_spmm_impl(bm_host, bm_dev, d, splits, xpack, dinv_row, (float *)Y, ldy, out_col_off, partial_ws, partial_bytes, s, true);
+}
+}  // namespace h2
+
+static int bm_spmm_impl(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
+                        const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
+                        size_t partial_bytes, h2_stream_t s, bool y_bf16) {
     cudaStream_t st = (cudaStream_t)s;
     const BmHost *h = (const BmHost *)bm_host;
     H2_REQUIRE(h && h->magic == kBmMagic && bm_dev && xpack && Y, H2_ERR_INVALID, "h2_bm_spmm_f32: bad plan / null argument");
@@ -1205,7 +1235,10 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
                "(h2_bm_fill_order)", h->bit_order, splits, i8 ? 1 : 0);
     const char *base = (const char *)bm_dev;
     if (h->n_empty_tiles > 0) {
-        bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, Y + out_col_off, ldy);
+        // bf16 rows: the same kernel zeroes d/2 "floats" per row of a buffer whose float stride is ldy/2
+        if (y_bf16) bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d / 2,
+                                                                                 (float *)((uint16_t *)Y + out_col_off), ldy / 2);
+        else bm_zero_tiles_kernel<<<(unsigned)h->n_empty_tiles, 256, 0, st>>>((const int32_t *)(base + h->off_empty_tiles), h->n_rows, d, Y + out_col_off, ldy);
         H2_LAUNCHED("bm_zero_tiles_kernel");
     }
     if (pair_applies(splits, d)) {
@@ -1224,7 +1257,8 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
         pp.xpack = (const uint8_t *)xpack + kI8HeaderBytes;
         pp.xstep = (const float *)xpack;
         pp.dinv_row = dinv_row;
-        pp.Y = Y + out_col_off;
+        pp.Y = y_bf16 ? (float *)((uint16_t *)Y + out_col_off) : Y + out_col_off;
+        pp.y_bf16 = y_bf16 ? 1 : 0;
         pp.partial = (float *)partial_ws;
         pp.sync = (uint32_t *)(const_cast<char *>(base) + sp.off_fix);        // the plan buffer holds the arrival counters
         {
@@ -1238,6 +1272,7 @@ extern "C" int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d
         pp.n_rows = h->n_rows; pp.d = d; pp.n_groups_fh = std::max(2, groups_for(d, fh));
         return pair_launch(splits_pieces(splits), fh, sp.n_ctas, pp, st);
     }
+    H2_REQUIRE(!y_bf16, H2_ERR_UNSUPPORTED, "h2_bm_spmm: bf16 rows are implemented for the int8 digits only");
     const int dg = dg_for(d, splits);
     const int n_groups = groups_for(d, dg);
     H2_REQUIRE(n_groups <= 8, H2_ERR_UNSUPPORTED, "h2_bm_spmm_f32: d=%d needs %d column groups (max 8): split the columns", d, n_groups);

@@ -90,7 +90,17 @@ struct BmPairParams {
     int32_t n_fix;
     int64_t ldy;
     int32_t n_rows, d, n_groups_fh;
+    int32_t y_bf16;              // Y rows hold bf16 (ldy counts bf16 elements): one rounding at the store
 };
+
+// 4 consecutive output features at element offset `off` of the Y buffer (fp32 rows or bf16 rows)
+__device__ __forceinline__ void pair_store4(float *Y, int64_t off, float4 v, int bf16) {
+    if (!bf16) { *reinterpret_cast<float4 *>(Y + off) = v; return; }
+    uint32_t lo, hi;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(Y) + off) = make_uint2(lo, hi);
+}
 
 #ifdef H2_BM_TRACE
 // per CTA: 0 start, 1 end, 2 MMA thread waits full_a, 3 MMA thread waits acc_empty, 4 / 5 producer warp 0 waits full_b /
@@ -388,8 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     } else {
                         const float sc = s_scale[row * kStageStride];
                         v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-                        if (col_ok && gr < p.n_rows)
-                            *reinterpret_cast<float4 *>(p.Y + gr * p.ldy + (int64_t)sg.group * (2 * FH) + fcol) = v;
+                        if (col_ok && gr < p.n_rows) pair_store4(p.Y, gr * p.ldy + (int64_t)sg.group * (2 * FH) + fcol, v, p.y_bf16);
                     }
                 }
             }
@@ -437,8 +446,8 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                             const int64_t gr = (int64_t)fx.tile * kTileRows + r0 + i * kRowsPerWarp;
                             if (gr < p.n_rows && c_ok) {
                                 const float sc = xstep * (p.dinv_row ? p.dinv_row[gr] : 1.f);
-                                *reinterpret_cast<float4 *>(p.Y + gr * p.ldy + (int64_t)fx.group * (2 * FH) + c) =
-                                    make_float4(v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc);
+                                pair_store4(p.Y, gr * p.ldy + (int64_t)fx.group * (2 * FH) + c,
+                                            make_float4(v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc), p.y_bf16);
                             }
                         }
                     }

@@ -294,7 +294,9 @@ extern "C" int h2_graph_formats(const h2_graph_t *g, int32_t *fmt_out) {
 namespace h2 {
 int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, const float *const *ptrs, const int64_t *bounds,
                   int64_t ld, const float *dinv_col, void *xpack, size_t xpack_bytes, float *xfull, int64_t ld_full,
-                  h2_stream_t s, bool zero_header);
+                  h2_stream_t s, bool zero_header, bool x_bf16);
+int bm_spmm_bf16_out(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack, const float *dinv_row,
+                     void *Y, int64_t ldy, int64_t out_col_off, void *partial_ws, size_t partial_bytes, h2_stream_t s);
 int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
                 float *xfull, int64_t ld_full, h2_stream_t s);
 }
@@ -310,8 +312,11 @@ struct RoundParts {   // the round input as row shards (device / peer pointers) 
 
 static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                             const int64_t *offsets, float *y_host, h2_stream_t s, const int64_t *x_offsets = nullptr,
-                            const RoundParts *parts = nullptr) {
+                            const RoundParts *parts = nullptr, int32_t x_dtype = H2_F32, int32_t y_dtype = H2_F32) {
     cudaStream_t st = (cudaStream_t)s;
+    const bool xb = x_dtype == H2_BF16, yb = y_dtype == H2_BF16;   // bf16 rows: ldx / ldy / offsets count bf16 elements
+    H2_REQUIRE(!(xb || yb) || (!parts && !x_offsets && !y_host && d % 8 == 0), H2_ERR_UNSUPPORTED,
+               "h2_graph_round_ex: bf16 rows are supported for plain device rounds with d %% 8 == 0");
     H2_REQUIRE(g && (X || parts) && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = H2_OK;
     H2_REQUIRE(!g->n_bm || (d <= g->d_max && g->xpack), H2_ERR_WORKSPACE,
@@ -337,7 +342,7 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
         if (g->n_bm && d <= max_w) {
             const int h = g->bm_idx[0];
             rc = bm_pack_parts(g->n_cols, d, g->splits, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, g->dinv[h],
-                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s, false);
+                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s, false, false);
             if (rc != H2_OK) return rc;
             first_bm = 1;
         } else {
@@ -360,12 +365,21 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
         for (int32_t c0 = 0; c0 < d; c0 += max_w) {
             const int32_t w = std::min(max_w, d - c0);
             if (!(k == 0 && first_bm)) {
-                rc = h2_bm_pack_x_f32_armed(g->n_cols, w, g->splits, X + (x_offsets ? x_offsets[h] : 0) + c0, ldx, g->dinv[h], g->xpack,
-                                      g->xpack_bytes, (h2_stream_t)bm_stream);
+                if (xb) {
+                    const float *xs = (const float *)((const uint16_t *)X + c0);
+                    const int64_t b2[2] = {0, g->n_cols};
+                    rc = bm_pack_parts(g->n_cols, w, g->splits, 1, &xs, b2, ldx, g->dinv[h], g->xpack, g->xpack_bytes, nullptr, 0,
+                                       (h2_stream_t)bm_stream, false, true);
+                } else {
+                    rc = h2_bm_pack_x_f32_armed(g->n_cols, w, g->splits, X + (x_offsets ? x_offsets[h] : 0) + c0, ldx, g->dinv[h], g->xpack,
+                                                g->xpack_bytes, (h2_stream_t)bm_stream);
+                }
                 if (rc != H2_OK) return rc;
             }
-            rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], w, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
-                                offsets[h] + c0, g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
+            if (yb) rc = bm_spmm_bf16_out(g->bm_host[h].data(), g->bm_dev[h], w, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
+                                          offsets[h] + c0, g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
+            else rc = h2_bm_spmm_f32(g->bm_host[h].data(), g->bm_dev[h], w, g->splits, g->xpack, g->dinv[h] + g->row_begin, Y, ldy,
+                                     offsets[h] + c0, g->partial, g->partial_bytes, (h2_stream_t)bm_stream);
             if (rc != H2_OK) return rc;
         }
     }
@@ -376,7 +390,8 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
             sub[k].out_col_off = offsets[g->csr_idx[k]];
             sub[k].in_col_off = x_offsets ? x_offsets[g->csr_idx[k]] : 0;
         }
-        rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy, s);
+        if (xb || yb) rc = h2_fused_hops_spmm_ex(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, x_dtype, Y, ldy, y_dtype, s);
+        else rc = h2_fused_hops_spmm_f32(g->plan_host.data(), g->plan_dev, g->n_rows, g->n_csr, sub, d, X, ldx, Y, ldy, s);
         if (rc != H2_OK) return rc;
         if (y_host)
             for (int k = 0; k < g->n_csr; ++k) {
@@ -409,6 +424,15 @@ extern "C" int h2_graph_round_parts(h2_graph_t *g, int32_t d, int32_t n_parts, c
 extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                               const int64_t *offsets, h2_stream_t s) {
     return graph_round_impl(g, d, X, ldx, Y, ldy, offsets, nullptr, s);
+}
+
+extern "C" int h2_graph_round_ex(h2_graph_t *g, int32_t d, const void *X, int64_t ldx, int32_t x_dtype, void *Y, int64_t ldy,
+                                 int32_t y_dtype, const int64_t *offsets, h2_stream_t s) {
+    H2_REQUIRE((x_dtype == H2_F32 || x_dtype == H2_BF16) && (y_dtype == H2_F32 || y_dtype == H2_BF16), H2_ERR_INVALID,
+               "h2_graph_round_ex: dtype codes are H2_F32 / H2_BF16");
+    H2_REQUIRE(!g || !g->n_bm || splits_is_i8(g->splits) || (x_dtype == H2_F32 && y_dtype == H2_F32), H2_ERR_UNSUPPORTED,
+               "h2_graph_round_ex: bf16 rows on the tensor-core hops need the int8 digits");
+    return graph_round_impl(g, d, (const float *)X, ldx, (float *)Y, ldy, offsets, nullptr, s, nullptr, nullptr, x_dtype, y_dtype);
 }
 
 extern "C" int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, const int64_t *x_offsets, float *Y,

@@ -39,8 +39,8 @@ struct __align__(16) RowDesc {   // one schedule slot: where the virtual row's e
 struct RoundParams {
     HopDev hop[H2_MAX_HOPS];
     const RowDesc *perm;   // [n_vrows] sorted by len descending; nullptr: natural order (plan-less callers)
-    const float *X;
-    float *Y;
+    const float *X;     // fp32 rows, or bf16 rows when x_bf16 (then ldx and the in offsets count bf16 elements)
+    float *Y;           // fp32 rows, or bf16 rows when y_bf16
     const float *bias;  // optional epilogue (sparse_dense): + bias[d], relu
     int64_t ldx, ldy;
     int64_t n_vrows;
@@ -49,7 +49,25 @@ struct RoundParams {
     int32_t n_hops;
     int32_t d4;  // d / 4
     int32_t relu;
+    int32_t x_bf16, y_bf16;   // BASELINE config 5: bf16 features in / out, fp32 accumulation
 };
+
+// 4 consecutive features of a row: one 16-byte fp32 load, or one 8-byte load of 4 bf16 widened to fp32
+__device__ __forceinline__ float4 load_x4(const float *row, int j, int bf16) {
+    if (!bf16) return __ldg(reinterpret_cast<const float4 *>(row) + j);
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(row) + j);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void store_y4(float *row, int j, float4 v, int bf16) {
+    if (!bf16) reinterpret_cast<float4 *>(row)[j] = v;
+    else reinterpret_cast<uint2 *>(row)[j] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
 
 // ---- plan kernels ----------------------------------------------------------------------------------------------
 struct HopPtrs {
@@ -101,7 +119,7 @@ template <int LPR, int NV>
 __device__ __forceinline__ void accumulate_segment(const int32_t *__restrict__ col, const float *__restrict__ val,
                                                    const float *__restrict__ dinv, int64_t s, int64_t e,
                                                    const float *__restrict__ X, int64_t ldx, int d4, int lane,
-                                                   float4 (&acc)[NV]) {
+                                                   float4 (&acc)[NV], int x_bf16) {
     constexpr int G = 32 / LPR;             // nonzeros processed side by side
     constexpr int U = (NV >= 4) ? 2 : ((NV == 2) ? 4 : 8);  // rows in flight per group
     const int grp = lane / LPR;
@@ -125,11 +143,13 @@ __device__ __forceinline__ void accumulate_segment(const int32_t *__restrict__ c
                 const float vv = __shfl_sync(0xffffffffu, v, idx & 31);
                 const bool on = idx < cnt;
                 w[u] = on ? vv : 0.f;
-                const float4 *xr = reinterpret_cast<const float4 *>(X + (int64_t)cc * ldx);
+                // row start: ldx counts elements of the row type (2-byte elements: half the float stride)
+                const float *xr = x_bf16 ? reinterpret_cast<const float *>(reinterpret_cast<const uint16_t *>(X) + (int64_t)cc * ldx)
+                                         : X + (int64_t)cc * ldx;
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
                     const int j = lig + q * LPR;
-                    x[u][q] = (on && j < d4) ? __ldg(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[u][q] = (on && j < d4) ? load_x4(xr, j, x_bf16) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
 #pragma unroll
@@ -205,18 +225,20 @@ fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     float4 acc[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_segment<LPR, NV>(hop.col, hop.val, hop.dinv, s, e, p.X + hop.in_off, p.ldx, p.d4, lane, acc);
+    const float *xbase = p.x_bf16 ? reinterpret_cast<const float *>(reinterpret_cast<const uint16_t *>(p.X) + hop.in_off) : p.X + hop.in_off;
+    accumulate_segment<LPR, NV>(hop.col, hop.val, hop.dinv, s, e, xbase, p.ldx, p.d4, lane, acc, p.x_bf16);
     reduce_groups<LPR, NV>(acc);
 
     const float scale = hop.val ? 1.f : __ldg(hop.dinv_row + i);  // factored mode: dinv_i * sum_j dinv_j x_j
-    float4 *yrow = reinterpret_cast<float4 *>(p.Y + (int64_t)i * p.ldy + hop.out_off);
+    float *yrow = p.y_bf16 ? reinterpret_cast<float *>(reinterpret_cast<uint16_t *>(p.Y) + (int64_t)i * p.ldy + hop.out_off)
+                           : p.Y + (int64_t)i * p.ldy + hop.out_off;
     const int lig = lane % LPR;
     if (!cta_row) {
         if (lane < LPR) {
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
                 const int j = lig + q * LPR;
-                if (j < p.d4) yrow[j] = epilogue(acc[q], scale, p.bias, j, p.relu);
+                if (j < p.d4) store_y4(yrow, j, epilogue(acc[q], scale, p.bias, j, p.relu), p.y_bf16);
             }
         }
         return;
@@ -236,7 +258,7 @@ fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
             const float4 t = s_part[w * p.d4 + j];
             a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
-        yrow[j] = epilogue(a, scale, p.bias, j, p.relu);
+        store_y4(yrow, j, epilogue(a, scale, p.bias, j, p.relu), p.y_bf16);
     }
 }
 
@@ -378,6 +400,7 @@ int fill_round_params(RoundParams &p, const PlanHost *ph, const void *plan_dev, 
     p.ldx = ldx; p.ldy = ldy;
     p.n_vrows = ph->n_vrows; p.n_cta_rows = ph->n_cta_rows;
     p.n_rows = n_rows; p.n_hops = n_hops; p.d4 = d / 4; p.relu = 0;
+    p.x_bf16 = 0; p.y_bf16 = 0;
     return H2_OK;
 }
 }  // namespace h2
@@ -390,6 +413,29 @@ extern "C" int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_de
     RoundParams p;
     int rc = fill_round_params(p, (const PlanHost *)plan_host, plan_dev, n_rows, n_hops, hops, d, X, ldx, Y, ldy);
     if (rc != H2_OK) return rc;
+    if (n_rows == 0) return H2_OK;
+    return run_gather_round(p, (cudaStream_t)s);
+}
+
+// same round with bf16 feature rows in and / or out (fp32 accumulation); ldx / ldy / offsets count elements of the row type
+extern "C" int h2_fused_hops_spmm_ex(const void *plan_host, const void *plan_dev, int32_t n_rows, int32_t n_hops,
+                                     const h2_hop_t *hops, int32_t d, const void *X, int64_t ldx, int32_t x_dtype, void *Y,
+                                     int64_t ldy, int32_t y_dtype, h2_stream_t s) {
+    H2_REQUIRE(n_hops >= 1 && n_hops <= H2_MAX_HOPS && n_rows >= 0, H2_ERR_INVALID, "fused round: n_rows=%d n_hops=%d",
+               n_rows, n_hops);
+    H2_REQUIRE((x_dtype == H2_F32 || x_dtype == H2_BF16) && (y_dtype == H2_F32 || y_dtype == H2_BF16), H2_ERR_INVALID,
+               "fused round: dtype codes are H2_F32 / H2_BF16");
+    const bool any16 = x_dtype == H2_BF16 || y_dtype == H2_BF16;
+    H2_REQUIRE(!any16 || d % 8 == 0, H2_ERR_ALIGN, "fused round: bf16 rows need d %% 8 == 0 (d=%d)", d);
+    H2_REQUIRE((x_dtype != H2_BF16 || ldx % 8 == 0) && (y_dtype != H2_BF16 || ldy % 8 == 0), H2_ERR_ALIGN,
+               "fused round: bf16 leading dimensions must be multiples of 8");
+    RoundParams p;
+    int rc = fill_round_params(p, (const PlanHost *)plan_host, plan_dev, n_rows, n_hops, hops, d, (const float *)X, ldx, (float *)Y, ldy);
+    if (rc != H2_OK) return rc;
+    for (int h = 0; h < n_hops; ++h)
+        H2_REQUIRE((x_dtype != H2_BF16 || hops[h].in_col_off % 8 == 0) && (y_dtype != H2_BF16 || hops[h].out_col_off % 8 == 0), H2_ERR_ALIGN,
+                   "fused round: bf16 column offsets must be multiples of 8");
+    p.x_bf16 = x_dtype == H2_BF16; p.y_bf16 = y_dtype == H2_BF16;
     if (n_rows == 0) return H2_OK;
     return run_gather_round(p, (cudaStream_t)s);
 }
@@ -441,5 +487,6 @@ extern "C" int h2_sparse_dense_f32(int32_t n_rows, const int64_t *rowptr, const 
     rp.ldx = p; rp.ldy = ldy;
     rp.n_vrows = n_rows; rp.n_cta_rows = 0;
     rp.n_rows = n_rows; rp.n_hops = 1; rp.d4 = p / 4; rp.relu = relu;
+    rp.x_bf16 = 0; rp.y_bf16 = 0;
     return run_gather_round(rp, (cudaStream_t)s);
 }

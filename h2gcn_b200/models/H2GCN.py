@@ -181,6 +181,7 @@ class _FusedProgram:
         self.final_width = sum(leaves[l]["width"] for l in cur)
         self.leaves, self.steps, self.off = leaves, steps, off
         self.buf = torch.empty(n_rows, self.total_width, dtype=torch.float32, device=device)
+        self._gbuf = None       # gradient twin of the concat buffer (training), allocated once
         self.adjhops = adjhops
         self.ok = True
 
@@ -202,12 +203,16 @@ class _FusedProgram:
         The aggregation rounds run backwards through the SAME fused kernels: A_h is symmetric, so dX = sum_h A_h dY_h
         with hop h reading its own slice of the gradient buffer (`HopPlan.run_multi`) and `sum_slices` adding them."""
         W_out = self.out_layer.kernel
-        gW_out = self._dropped.t() @ dlogits                      # [W, C] dense contraction (library GEMM)
-        gfinal = dlogits @ W_out.t()
+        # the two classifier-side contractions on the tcgen05 kernel (h2_dense_tc_f32, transposed forms): dW = final^T dlogits
+        # and dfinal = dlogits W^T, the latter written straight into the gradient buffer
+        gW_out = ops.matmul(self._dropped, dlogits, trans_a=True)            # [W, C]
+        gbuf = self._gbuf
+        if gbuf is None or gbuf.shape != self.buf.shape:
+            gbuf = self._gbuf = torch.empty_like(self.buf)
+        gbuf.zero_()
+        ops.matmul(dlogits, W_out, trans_w=True, out=gbuf)                   # [N, W] into columns [0, final_width)
         if self._mask is not None:
-            gfinal = gfinal * self._mask
-        gbuf = torch.zeros_like(self.buf)
-        gbuf[:, :self.final_width] = gfinal
+            gbuf[:, :self.final_width].mul_(self._mask)
         gW0 = None
         for lid in reversed(self.steps):
             lf, o = self.leaves[lid], self.off[lid]

@@ -67,10 +67,21 @@ class SparseDense(_Named):
     def weights(self):
         return [w for w in (self.kernel, self.bias) if w is not None]
 
+    # a feature matrix at least this dense is a true dense contraction (syn-products / ogbn features):
+    # it is densified once and goes through the tensor-core kernel instead of the CSR gather
+    DENSE_THRESHOLD = 0.25
+
     def __call__(self, input, relu=False, out=None, out_col_off=0):
         if self.kernel is None:
             self.build(input.shape, input.device)
-        y = ops.sparse_dense(input, self.kernel, self.bias, relu=relu, out=out, out_col_off=out_col_off)
+        n, f = input.dense_shape
+        if n and f and input.nnz >= self.DENSE_THRESHOLD * n * f:
+            xd = input.__dict__.get("_dense")
+            if xd is None:
+                xd = input.__dict__["_dense"] = ToDense()(input)
+            y = ops.matmul(xd, self.kernel, bias=self.bias, relu=relu, out=out, out_col_off=out_col_off)
+        else:
+            y = ops.sparse_dense(input, self.kernel, self.bias, relu=relu, out=out, out_col_off=out_col_off)
         if self.activation:
             y = self.activation(y)
         return y

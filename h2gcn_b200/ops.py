@@ -235,8 +235,9 @@ class HopPlan:
     def run(self, x, out, offsets, d=None, stream=None):
         """out[:, offsets[h] : offsets[h]+d] = hops[h] @ x[:, :d]   (x, out may be column slices of one buffer)."""
         require_cuda(x, out)
-        if x.dtype != torch.float32 or out.dtype != torch.float32:
-            raise ValueError("fused round computes in fp32")
+        dt = {torch.float32: _cabi.H2_F32, torch.bfloat16: _cabi.H2_BF16}
+        if x.dtype not in dt or out.dtype not in dt:
+            raise ValueError("fused round: fp32 or bf16 feature matrices (accumulation is fp32 / exact int32 either way)")
         if x.stride(-1) != 1 or out.stride(-1) != 1:
             raise ValueError("x / out must be row-major (unit column stride)")
         d = x.shape[1] if d is None else d
@@ -245,13 +246,19 @@ class HopPlan:
                              f"[{self.n_rows}, {self.n_cols}]")
         if len(offsets) != len(self.hops):
             raise ValueError("one output column offset per hop")
-        if d % 4 or x.stride(0) % 4 or out.stride(0) % 4 or any(o % 4 or o < 0 or o + d > out.stride(0) for o in offsets) \
+        bf = x.dtype == torch.bfloat16 or out.dtype == torch.bfloat16
+        q = 8 if bf else 4                      # rows are moved 16 bytes at a time
+        if d % q or x.stride(0) % q or out.stride(0) % q or any(o % q or o < 0 or o + d > out.stride(0) for o in offsets) \
                 or x.data_ptr() % 16 or out.data_ptr() % 16:
-            raise ValueError(f"fused round: d={d}, leading dimensions and column offsets must be multiples of 4 "
+            raise ValueError(f"fused round: d={d}, leading dimensions and column offsets must be multiples of {q} "
                              "and the buffers 16-byte aligned")
         offs = (ctypes.c_int64 * len(offsets))(*offsets)
         self.reserve(d)
-        check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(out), out.stride(0), offs, stream_ptr(stream)))
+        if bf:    # BASELINE config 5: bf16 features in / out
+            check(lib().h2_graph_round_ex(self._h, d, ptr(x), x.stride(0), dt[x.dtype], ptr(out), out.stride(0), dt[out.dtype],
+                                          offs, stream_ptr(stream)))
+        else:
+            check(lib().h2_graph_round(self._h, d, ptr(x), x.stride(0), ptr(out), out.stride(0), offs, stream_ptr(stream)))
         return out
 
     def run_multi(self, x, x_offsets, out, offsets, d, stream=None):
@@ -319,20 +326,41 @@ def sparse_dense(feat, weight, bias=None, relu=False, out=None, out_col_off=0, s
     return out
 
 
-def dense(x, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None):
-    """keras Dense (H2GCN.py:244-249): out[:, off:off+c] = act(x @ weight + bias), fp32."""
-    require_cuda(x, weight, bias, out)
-    n, k = x.shape
-    c = weight.shape[1]
-    if weight.shape[0] != k:
-        raise ValueError(f"input dim {k} != kernel rows {weight.shape[0]}")
-    if x.stride(-1) != 1:
-        x = x.contiguous()
-    weight = weight.contiguous()
+def dense(x, weight, bias=None, relu=False, out=None, out_col_off=0, stream=None, mode="tc"):
+    """keras Dense (H2GCN.py:244-249): out[:, off:off+c] = act(x @ weight + bias), fp32 in / out.
+    mode="tc" (default): tcgen05 3xTF32 kernel (fp32-equivalent); mode="simt": the fp32 SIMT kernel with the oracle's
+    sequential-k summation order (parity mode)."""
+    return matmul(x, weight, bias=bias, relu=relu, out=out, out_col_off=out_col_off, stream=stream, mode=mode)
+
+
+def matmul(a, w, trans_a=False, trans_w=False, bias=None, relu=False, out=None, out_col_off=0, stream=None, mode="tc"):
+    """out[:, off:off+n] = act(op(a) @ op(w) + bias): op = transpose when the flag is set (a: [k, m], w: [n, k]).  `a` and
+    `w` may be column slices of wider row-major buffers.  The transposed forms are the classifier-side contractions of
+    the training step (dW = final^T dlogits, dfinal = dlogits W^T)."""
+    require_cuda(a, w, bias, out)
+    if a.dtype != torch.float32 or w.dtype != torch.float32:
+        raise ValueError("dense contraction computes in fp32")
+    if a.stride(-1) != 1:
+        a = a.contiguous()
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    m, k = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    n, kw = (w.shape[0], w.shape[1]) if trans_w else (w.shape[1], w.shape[0])
+    if kw != k:
+        raise ValueError(f"input dim {k} != kernel rows {kw}")
     if out is None:
-        out = torch.empty(n, c, dtype=torch.float32, device=x.device)
-    check(lib().h2_dense_f32(n, k, c, ptr(x), x.stride(0), ptr(weight), ptr(bias), int(relu), ptr(out), out.stride(0),
-                             out_col_off, stream_ptr(stream)))
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    if mode == "simt":
+        if trans_a or trans_w:
+            raise ValueError("the SIMT parity kernel has no transposed forms")
+        w = w.contiguous()
+        check(lib().h2_dense_f32(m, k, n, ptr(a), a.stride(0), ptr(w), ptr(bias), int(relu), ptr(out), out.stride(0),
+                                 out_col_off, stream_ptr(stream)))
+    elif mode == "tc":
+        check(lib().h2_dense_tc_f32(m, k, n, ptr(a), a.stride(0), int(trans_a), ptr(w), w.stride(0), int(trans_w), ptr(bias),
+                                    int(relu), ptr(out), out.stride(0), out_col_off, stream_ptr(stream)))
+    else:
+        raise ValueError(f"unknown mode {mode}")
     return out
 
 

@@ -42,6 +42,10 @@ enum {
 
 #define H2_MAX_HOPS 8
 
+/* element type of the dense feature matrices of a round (BASELINE config 5: bf16 features, fp32 accumulation) */
+#define H2_F32 0
+#define H2_BF16 1
+
 typedef void *h2_stream_t; /* cudaStream_t */
 typedef struct h2_graph h2_graph_t;
 
@@ -127,6 +131,13 @@ int h2_fused_hops_spmm_f32(const void *plan_host, const void *plan_dev, int32_t 
                            const h2_hop_t *hops_host, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                            h2_stream_t s);
 
+/* Same round with bf16 feature rows in and / or out (x_dtype / y_dtype = H2_F32 | H2_BF16), fp32 accumulation, one rounding
+ * to bf16 at the store.  Leading dimensions and column offsets count ELEMENTS of the row type; bf16 rows need d, ld and
+ * offsets to be multiples of 8 (16-byte rows). */
+int h2_fused_hops_spmm_ex(const void *plan_host, const void *plan_dev, int32_t n_rows, int32_t n_hops,
+                          const h2_hop_t *hops_host, int32_t d, const void *X, int64_t ldx, int32_t x_dtype, void *Y,
+                          int64_t ldy, int32_t y_dtype, h2_stream_t s);
+
 /* ---- a6 on the tensor cores: dense-ish BINARY hop patterns in "tile bitmap" format ------------------------------
  *   For a hop whose normalised values factor as dinv_row[i] * dinv_col[j] over a 0/1 pattern
  * (every SYM/RW-normalised nhoodSplit ring), Y = diag(dinv_row) . P . (diag(dinv_col) . X) is evaluated with
@@ -168,6 +179,10 @@ size_t h2_bm_xpack_bytes(int32_t n_cols, int32_t d, int32_t splits);
 size_t h2_bm_partial_bytes(const void *bm_host, int32_t d, int32_t splits);
 int h2_bm_pack_x_f32(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx, const float *dinv_col,
                      void *xpack, size_t xpack_bytes, h2_stream_t s);
+/* same, for a buffer whose first 256 bytes were zeroed once and which only ever went through these pack calls (the int8
+ * pack kernel keeps its grid-barrier counters there and re-arms them itself): no memset per call */
+int h2_bm_pack_x_f32_armed(int32_t n_cols, int32_t d, int32_t splits, const float *X, int64_t ldx, const float *dinv_col,
+                           void *xpack, size_t xpack_bytes, h2_stream_t s);
 int h2_bm_spmm_f32(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack,
                    const float *dinv_row, float *Y, int64_t ldy, int64_t out_col_off, void *partial_ws,
                    size_t partial_bytes, h2_stream_t s);
@@ -181,6 +196,13 @@ int h2_sparse_dense_f32(int32_t n_rows, const int64_t *rowptr, const int32_t *co
 /* replaces keras Dense (H2GCN.py:244-249): Y[n, c] = act(X[n, k] . W[k, c] + b), fp32 SIMT (parity mode). */
 int h2_dense_f32(int32_t n_rows, int32_t k, int32_t c, const float *X, int64_t ldx, const float *W, const float *bias,
                  int32_t relu, float *Y, int64_t ldy, int64_t out_col_off, h2_stream_t s);
+/* The same contraction on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split: fp32-equivalent, ~3e-7 of max-abs):
+ * Y[m, off:off+n] = act(op(A) . op(W) + b) with A [m, k] (trans_a == 0) or [k, m] (trans_a != 0), W [k, n] (trans_w == 0)
+ * or [n, k] (trans_w != 0), all fp32 row-major with leading dimensions in elements.  Default path of the classifier
+ * (H2GCN.py:244-257), of SparseDense on dense features (_layers.py:45-52) and of the classifier-side contractions of the
+ * training step (dW = final^T . dlogits: trans_a; dfinal = dlogits . W^T: trans_w).  No alignment requirements. */
+int h2_dense_tc_f32(int32_t m, int32_t k, int32_t n, const float *A, int64_t lda, int32_t trans_a, const float *W, int64_t ldw,
+                    int32_t trans_w, const float *bias, int32_t relu, float *Y, int64_t ldy, int64_t out_col_off, h2_stream_t s);
 /* ReLU / copy of a column slice (layers the planner could not fuse away). */
 int h2_relu_slice_f32(int32_t n_rows, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy, int32_t relu,
                       h2_stream_t s);
@@ -216,6 +238,12 @@ int h2_graph_round_host(h2_graph_t *g, int32_t d, const float *x_host, float *y_
 /* same round on DEVICE buffers (X [n_cols, d] ld=ldx; Y: hop h at column offsets[h]); enqueues, does not synchronise. */
 int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,
                    const int64_t *offsets_host, h2_stream_t s);
+/* the round with bf16 feature rows (BASELINE config 5): X and / or Y hold bf16 (H2_BF16), accumulation is fp32 (CSR hops)
+ * or exact int32 over the int8 digits of X' (tensor-core hops: the bf16 input is exactly representable in the digits'
+ * 16 / 24 bits up to the row scaling, so the only rounding of the round is the final fp32 -> bf16 store).  int8 `splits`
+ * only; d, ldx, ldy and the offsets are multiples of 8 elements. */
+int h2_graph_round_ex(h2_graph_t *g, int32_t d, const void *X, int64_t ldx, int32_t x_dtype, void *Y, int64_t ldy,
+                      int32_t y_dtype, const int64_t *offsets_host, h2_stream_t s);
 /* backward-style round: hop h reads X[:, x_offsets[h] : +d] (its own slice) and writes Y[:, y_offsets[h] : +d]. */
 int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, const int64_t *x_offsets_host, float *Y,
                          int64_t ldy, const int64_t *y_offsets_host, h2_stream_t s);

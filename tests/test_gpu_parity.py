@@ -783,3 +783,98 @@ def test_training_refuses_dropout_that_does_not_feed_the_classifier(dev):
     good = H2GCN(parse_network_setup("M64-R-T1-G-V-C1-D0.5-MO", C, _dense_units=64, _dropout_rate=0.5))
     loss, grads = good.loss_and_grads(t.adj, t.features, t.adj_hops, y, m)
     assert np.isfinite(loss) and len(grads) == 2
+
+
+# ---- f2: dense ends on the tensor cores (tcgen05 kind::tf32, 3xTF32) ------------------------------------------------------
+@pytest.mark.parametrize("m,k,n", [(2708, 448, 7), (2708, 192, 6), (10000, 100, 64), (130, 33, 5), (128, 8, 16), (1, 1, 1),
+                                   (3000, 1433, 64), (700, 448, 40), (513, 96, 200)])
+def test_dense_tc_matches_fp64(dev, m, k, n):
+    """h2_dense_tc_f32 against an fp64 product: the 3xTF32 split drops only 2^-21 terms; what remains is the tensor core's
+    round-toward-zero fp32 accumulation, one truncation per MMA instruction (K = 8), i.e. a bias of <= K/8 * 3 * 2^-24 —
+    measured 4.4e-6 of max-abs at K = 448 (bar 1e-5; the north-star tolerance is 1e-4).  With bias + ReLU, writing into a
+    column slot of a wider buffer; the SIMT parity kernel (sequential-k fp32, ~1e-6) for comparison."""
+    from h2gcn_b200 import ops
+    rng = np.random.default_rng(m + k + n)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    ad, wd, bd = (torch.from_numpy(t).to(dev) for t in (a, w, b))
+    ref = a.astype(np.float64) @ w.astype(np.float64)
+    y = ops.matmul(ad, wd)
+    assert util.rel_err(y.cpu().numpy(), ref) <= 1e-5
+    buf = torch.full((m, n + 9), 7.0, device=dev)
+    ops.matmul(ad, wd, bias=bd, relu=True, out=buf, out_col_off=5)
+    got = buf.cpu().numpy()
+    assert util.rel_err(got[:, 5:5 + n], np.maximum(ref + b, 0)) <= 1e-5
+    assert (got[:, :5] == 7.0).all() and (got[:, 5 + n:] == 7.0).all()
+    ys = ops.dense(ad, wd, mode="simt")
+    assert util.rel_err(ys.cpu().numpy(), ref) <= 2e-6
+    # inputs that are column slices of a wider buffer (the concat buffer), misaligned by one float
+    wide = torch.zeros(m, k + 3, device=dev)
+    wide[:, 1:1 + k] = ad
+    assert util.rel_err(ops.matmul(wide[:, 1:1 + k], wd).cpu().numpy(), ref) <= 1e-5
+
+
+def test_dense_tc_transposed_forms(dev):
+    """dW = final^T dlogits (trans_a) and dfinal = dlogits W^T (trans_w): the classifier-side contractions of training."""
+    from h2gcn_b200 import ops
+    rng = np.random.default_rng(0)
+    n, wdt, c = 2708, 448, 7
+    final = rng.standard_normal((n, wdt)).astype(np.float32)
+    dl = rng.standard_normal((n, c)).astype(np.float32)
+    W = rng.standard_normal((wdt, c)).astype(np.float32)
+    fd, dld, Wd = (torch.from_numpy(t).to(dev) for t in (final, dl, W))
+    g = ops.matmul(fd, dld, trans_a=True)
+    assert g.shape == (wdt, c) and util.rel_err(g.cpu().numpy(), final.astype(np.float64).T @ dl.astype(np.float64)) <= 2e-5
+    gf = ops.matmul(dld, Wd, trans_w=True)
+    assert gf.shape == (n, wdt) and util.rel_err(gf.cpu().numpy(), dl.astype(np.float64) @ W.astype(np.float64).T) <= 1e-5
+
+
+def test_dense_features_take_the_tensor_core_gemm(dev):
+    """syn-products style DENSE features (configs/syn-products/h2gcn.json, --no_feature_normalize): SparseDense densifies
+    them once and X W0 (+ReLU) runs on the tcgen05 kernel, writing into its concat slot."""
+    from h2gcn_b200 import _cabi
+    from h2gcn_b200.models import _layers as L
+    from h2gcn_b200.ops import SparseTensor
+    rng = np.random.default_rng(3)
+    n, F, p = 4000, 100, 64
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    feat = SparseTensor.from_scipy(sp.csr_matrix(x), dev)
+    layer = L.SparseDense(p)
+    layer.build((n, F), dev)
+    buf = torch.zeros(n, 3 * p, device=dev)
+    before = _cabi.launch_count()
+    layer(feat, relu=True, out=buf, out_col_off=p)
+    layer(feat, relu=True, out=buf, out_col_off=p)
+    ref = np.maximum(x.astype(np.float64) @ layer.kernel.cpu().numpy().astype(np.float64), 0)
+    assert util.rel_err(buf[:, p:2 * p].cpu().numpy(), ref) <= 1e-5
+    assert (buf[:, :p] == 0).all() and (buf[:, 2 * p:] == 0).all()
+    assert _cabi.launch_count() - before == 2, "one tensor-core launch per call (the dense copy is cached)"
+
+
+# ---- g2: bf16 feature rows in / out (BASELINE config 5) ---------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["csr", "tensor", "auto"])
+@pytest.mark.parametrize("d", [8, 64, 128, 256])
+def test_bf16_feature_rows(dev, mode, d):
+    """X and Y in bf16, fp32 accumulation (CSR hops) / exact int32 over the digits (tensor-core hops), ONE rounding to bf16
+    at the store.  Reference: the fp64 product of the bf16-rounded input; bar = half a bf16 ulp of the result (2^-9
+    relative per element, stated norm-wise as 4e-3 of max-abs) — the only error source besides fp32 accumulation order."""
+    from h2gcn_b200.ops import HopPlan
+    z = util.load_golden("planetoid_cora")
+    n = int(z["feat_shape"][0])
+    hops = _norm_hops(dev, z)
+    x = torch.from_numpy(np.random.default_rng(d).standard_normal((n, d)).astype(np.float32)).to(dev).to(torch.bfloat16)
+    ref = np.concatenate([sp.csr_matrix((v.astype(np.float64), (r, c)), shape=(n, n)) @ x.float().cpu().numpy().astype(np.float64)
+                          for r, c, v in util.golden_hops(z)], axis=1)
+    y = torch.full((n, 2 * d + 8), float("nan"), device=dev, dtype=torch.bfloat16)
+    HopPlan(hops, mode=mode).run(x, y, [0, d + 8])
+    got = y.float().cpu().numpy()
+    got = np.concatenate([got[:, :d], got[:, d + 8:]], axis=1)
+    err = np.abs(got - ref)
+    assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-6 * np.abs(ref).max()).all(), "within one bf16 rounding of the exact result, element-wise"
+    assert util.rel_err(got, ref) <= 4e-3
+    assert torch.isnan(y[:, d:d + 8].float()).all(), "columns outside the slots are untouched"
+    # mixed: bf16 in, fp32 out
+    y32 = torch.empty(n, 2 * d, device=dev)
+    HopPlan(hops, mode=mode).run(x, y32, [0, d])
+    assert util.rel_err(y32.cpu().numpy(), ref) <= 1e-5
