@@ -13,12 +13,14 @@
 // against an fp64 product, bar 1e-5 (north-star tolerance 1e-4).  The fp32 SIMT kernel h2_dense_f32 stays as the
 // reference-order parity mode.
 //
-// Per CTA (160 threads): 128 rows of the output (UMMA M = 128), N = c padded to a multiple of 16 (tiles of <= 128 columns).
-//   warps 0..3 : loaders — 128-bit coalesced global loads of a [128 x 32] fp32 slab of A (a K block = one 128-byte
+// Per CTA (288 threads): 128 rows of the output (UMMA M = 128), N = c padded to a multiple of 16 (tiles of <= 128 columns).
+//   warps 0..7 : loaders, two groups of 4 on alternate K blocks, each with its NEXT block's global loads already in flight
+//                in registers (4 K blocks of loads outstanding per CTA: with one group and no prefetch the kernel paid one
+//                DRAM round trip per K block, 42 us for the Cora classifier under ncu) — — 128-bit coalesced global loads of a [128 x 32] fp32 slab of A (a K block = one 128-byte
 //                swizzle row), split, two `st.shared.v4` into the K-major SWIZZLE_128B images of A_big / A_small; the W
 //                slab likewise (scalar stores: it is tiny and arrives transposed); `fence.proxy.async` + mbarrier arrive.
 //                Afterwards the epilogue: `tcgen05.ld` (lane = row), + bias, ReLU, stores into the concat slot.
-//   warp 4     : allocates TMEM; one elected lane issues 4 K steps x 3 MMAs per K block and commits the stage.
+//   warp 8     : allocates TMEM; one elected lane issues 4 K steps x 3 MMAs per K block and commits the stage.
 // The op is HBM / latency bound (Cora classifier: 4.9 MB in, 76 KB out), so the loaders ARE the pipeline: 3-4 stages.
 #include "bm_common.cuh"
 
@@ -26,7 +28,9 @@ namespace h2 {
 
 constexpr int kDtRows = 128;        // UMMA M
 constexpr int kDtKBlock = 32;       // fp32 per K block = 128 bytes = one SWIZZLE_128B row
-constexpr int kDtLoaders = 128;
+constexpr int kDtGroup = 128;       // loader threads per K block (one group fills one stage)
+constexpr int kDtGroups = 2;        // loader groups: group g takes the K blocks kb = g (mod 2)
+constexpr int kDtLoaders = kDtGroup * kDtGroups;
 constexpr int kDtThreads = kDtLoaders + 32;
 
 struct DenseTcParams {
@@ -82,13 +86,13 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_full + 8 * s, kDtLoaders);
+            mbar_init(bar_full + 8 * s, kDtGroup);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kDtLoaders / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    if (warp == 4) {
+    if (warp == kDtLoaders / 32) {
         // ===== MMA issuer =====
         if (elect_one()) {
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -120,47 +124,54 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
         __syncwarp();
     } else {
         // ===== loaders =====
-        const int t = threadIdx.x;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        const int grp = threadIdx.x / kDtGroup, t = threadIdx.x % kDtGroup;
+        // the [128 x 32] fp32 slab of K block kb as 8 float4 per thread (8 lanes cover the 128 bytes of a row: coalesced)
+        auto load_a = [&](int kb, float4 (&va)[8]) {
+            const int k0 = kb * kDtKBlock;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = t + i * kDtGroup, r = idx >> 3, c4 = (idx & 7) * 4;
+                const int64_t gr = m0 + r;
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < p.m && kb < n_kb) {
+                    const float *src = p.A + gr * p.lda + k0 + c4;
+                    if (k0 + c4 + 4 <= p.k && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) va[i] = *reinterpret_cast<const float4 *>(src);
+                    else {
+                        if (k0 + c4 + 0 < p.k) va[i].x = src[0];
+                        if (k0 + c4 + 1 < p.k) va[i].y = src[1];
+                        if (k0 + c4 + 2 < p.k) va[i].z = src[2];
+                        if (k0 + c4 + 3 < p.k) va[i].w = src[3];
+                    }
+                }
+            }
+        };
+        float4 va[2][8];
+        if (!p.trans_a) load_a(grp, va[0]);
+        int buf = 0;
+        for (int kb = grp; kb < n_kb; kb += kDtGroups, buf ^= 1) {
             const uint32_t s = kb % kStages;
             const int k0 = kb * kDtKBlock;
             uint8_t *a_big = smem_gen + s * kStageBytes, *a_small = a_big + kABytes;
             uint8_t *b_big = a_small + kABytes, *b_small = b_big + kBBytes;
-            // global loads first (they do not touch the stage), then wait for the stage to be free
-            float4 va[8];
-            if (!p.trans_a) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {                 // 8 lanes cover the 128 bytes of a row: coalesced
-                    const int idx = t + i * kDtLoaders, r = idx >> 3, c4 = (idx & 7) * 4;
-                    const int64_t gr = m0 + r;
-                    va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gr < p.m) {
-                        const float *src = p.A + gr * p.lda + k0 + c4;
-                        if (k0 + c4 + 4 <= p.k && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) va[i] = *reinterpret_cast<const float4 *>(src);
-                        else {
-                            if (k0 + c4 + 0 < p.k) va[i].x = src[0];
-                            if (k0 + c4 + 1 < p.k) va[i].y = src[1];
-                            if (k0 + c4 + 2 < p.k) va[i].z = src[2];
-                            if (k0 + c4 + 3 < p.k) va[i].w = src[3];
-                        }
-                    }
-                }
+            if (!p.trans_a) {                    // this group's NEXT block: its loads fly while the current one is split
+                if (buf == 0) load_a(kb + kDtGroups, va[1]); else load_a(kb + kDtGroups, va[0]);
             }
             mbar_wait(bar_empty + 8 * s, ((kb / kStages) & 1) ^ 1);
             if (!p.trans_a) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int idx = t + i * kDtLoaders, r = idx >> 3, c4 = (idx & 7) * 4;
+                    const int idx = t + i * kDtGroup, r = idx >> 3, c4 = (idx & 7) * 4;
+                    const float4 v = buf == 0 ? va[0][i] : va[1][i];
                     float4 b, sm;
-                    split_tf32(va[i].x, b.x, sm.x); split_tf32(va[i].y, b.y, sm.y);
-                    split_tf32(va[i].z, b.z, sm.z); split_tf32(va[i].w, b.w, sm.w);
+                    split_tf32(v.x, b.x, sm.x); split_tf32(v.y, b.y, sm.y);
+                    split_tf32(v.z, b.z, sm.z); split_tf32(v.w, b.w, sm.w);
                     const uint32_t off = sw128_off(r, c4);
                     *reinterpret_cast<float4 *>(a_big + off) = b;
                     *reinterpret_cast<float4 *>(a_small + off) = sm;
                 }
             } else {
                 // A given as [k, m]: element (row r, k) = A[(k0 + k) * lda + m0 + r]; consecutive threads read consecutive m
-                for (int idx = t; idx < kDtKBlock * kDtRows; idx += kDtLoaders) {
+                for (int idx = t; idx < kDtKBlock * kDtRows; idx += kDtGroup) {
                     const int kq = idx / kDtRows, r = idx % kDtRows;
                     float v = 0.f;
                     if (k0 + kq < p.k && m0 + r < p.m) v = p.A[(int64_t)(k0 + kq) * p.lda + m0 + r];
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
                 }
             }
             // W slab: B[n][k] (K-major) = W[k0 + k][n0 + n] (or W[n0 + n][k0 + k] when it is given transposed)
-            for (int idx = t; idx < kDtKBlock * NT; idx += kDtLoaders) {
+            for (int idx = t; idx < kDtKBlock * NT; idx += kDtGroup) {
                 int kq, nn;
                 if (!p.trans_w) { kq = idx / NT; nn = idx % NT; } else { nn = idx / kDtKBlock; kq = idx % kDtKBlock; }
                 float v = 0.f;
@@ -190,10 +201,11 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
         // ===== epilogue: lane = row =====
         mbar_wait(bar_acc, 0);
         tc_fence_after();
-        const int64_t gr = m0 + warp * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int quarter = warp & 3, chalf = warp >> 2;     // TMEM lane quarter of this warp, and which 16-column blocks it takes
+        const int64_t gr = m0 + quarter * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
+        for (int c0 = 16 * chalf; c0 < NT; c0 += 16 * kDtGroups) {
             uint32_t acc[16], acc2[16];
             cuda::ptx::tcgen05_ld_32x32b(acc, t_lane + c0);
             cuda::ptx::tcgen05_ld_32x32b(acc2, t_lane + NT + c0);
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kDtLoaders / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
