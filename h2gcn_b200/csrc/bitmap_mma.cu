@@ -834,7 +834,7 @@ static I8Layout i8_layout(int32_t n_cols, int32_t d, int32_t splits) {
 }
 
 // ---- CTA-pair int8 kernel (bm_pair.cu) ----
-struct BmPairSeg { int32_t tile, unit_begin, unit_end, group, role, slot, fix, pad1; };
+struct BmPairSeg { int32_t tile, unit_begin, unit_end, group, n_slots, slot, fix, slot_begin; };
 struct BmPairFix { int32_t tile, group, slot_begin, n_slots; };
 struct BmPairParams {
     const int32_t *unit_chunk; const unsigned long long *bits; const BmPairSeg *seg; const int32_t *cta_seg_ptr;

@@ -27,6 +27,8 @@
 // rotate+mask words -> `tcgen05.st` -> wait::st -> remote arrive on the leader's barrier), then epilogue; warp 8 = TMA
 // (`cp.async.bulk`: B half + expansion constants + 1 KB of bitmap per unit); warp 9 = TMEM allocation and, in the
 // leader CTA, the ONE thread that issues every MMA / commit for both CTAs.
+#include <stdlib.h>
+
 #include "bm_common.cuh"
 
 namespace h2 {
@@ -38,14 +40,12 @@ constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;    // 320
 constexpr int kPairMaxRegs = 144;
 constexpr int kPairMaxSegUnits = 2048;                      // int32 accumulators: 2^17 columns of at most 64 * 128
 
-enum : int32_t { kRoleWhole = 0, kRoleSender = 1 };
-
 struct BmPairSeg {        // one contiguous run of units inside one (row tile, column group), handled by one CTA pair
     int32_t tile, unit_begin, unit_end, group;
-    int32_t role;         // kRoleWhole: writes Y; kRoleSender: part of a split item, writes partial slot `slot`
-    int32_t slot;
-    int32_t fix;          // sender: index of the item in the fix list
-    int32_t pad1;
+    int32_t n_slots;      // 0: the segment covers its whole item and writes Y; else the item is split into n_slots segments
+    int32_t slot;         // split item: this segment's partial slot (slots of an item are consecutive, unit order)
+    int32_t fix;          // split item: index of the item (arrival counters)
+    int32_t slot_begin;   // split item: first slot of the item
 };
 
 struct BmPairFix {        // one split (tile, group) item: Y rows = scale * sum of slots [slot_begin, slot_begin + n_slots)
@@ -142,6 +142,12 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride, kBitsBytes = Cfg::kBitsBytes;
     constexpr uint32_t kACol0 = Cfg::kACol0, kTmemCols = 512;
     constexpr int kAStg = Cfg::kAStg, kBStg = Cfg::kBStg, kStageStride = Cfg::kStageStride;
+#ifdef H2_BM_PAIR_AHEAD
+    constexpr int kAhead = H2_BM_PAIR_AHEAD;
+#else
+    constexpr int kAhead = (kAStg < kBStg ? kAStg : kBStg) - 2;
+#endif
+    static_assert(kAhead >= 0 && kAhead < kAStg && kAhead < kBStg, "run-ahead must stay inside both rings");
     // D int32 | A, B signed int8 | N | M = 256 (128 rows per CTA)
     constexpr uint32_t kN1 = Cfg::kTwoInstr ? 256 : N, kN2 = N - kN1;
     constexpr uint32_t kIdesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((kN1 >> 3) << 17) | ((256u >> 4) << 24);
@@ -283,12 +289,12 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
         const float xstep = __ldg(p.xstep);
         uint32_t it = 0, acc_it = 0;   // units / accumulator phases before this segment
         PT_DECL();
-        for (int w = 0; w < n_work; ++w, ++acc_it) {
-            const BmPairSeg sg = p.seg[seg_begin + w];
-            const int n_units = sg.unit_end - sg.unit_begin;
-            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it % kPairGroups)) % kPairGroups);
-            for (int hnd = skip; hnd < n_units; hnd += kPairGroups) {        // this group's units
-                const uint32_t iu = it + (uint32_t)hnd;
+        // this group's units hnd in [from, to) of a segment whose first unit is the it0-th unit of this CTA pair
+        auto produce = [&](uint32_t it0, int from, int to) {
+            const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it0 % kPairGroups)) % kPairGroups);
+            const int first = from + (int)((uint32_t)(skip + kPairGroups - from % kPairGroups) % kPairGroups);
+            for (int hnd = first; hnd < to; hnd += kPairGroups) {
+                const uint32_t iu = it0 + (uint32_t)hnd;
                 const uint32_t sb = iu % kBStg, pb = (iu / kBStg) & 1;
                 { PT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); PT_END(0); }
 #ifdef H2_BM_TRACE
@@ -329,7 +335,25 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                 if (quarter == 0 && lane == 0) PT_UNIT(4, iu);
 #endif
             }
+        };
+        // Run-ahead: before the epilogue of segment w the producers already stage the first kAhead units of segment
+        // w + 1 (their A stages become free as the MMA thread works through the LAST units of w, so nothing here waits
+        // for the epilogue), then drain the accumulators while the MMA thread still has ~2 units of w to go.  The tensor
+        // pipe restarts on w + 1 the moment the accumulators are free instead of after the write-out + one production
+        // round trip (r02c trace: ~5 k idle cycles per segment boundary before).  kAhead < ring depths: unit k of
+        // w + 1 needs the MMA of unit (k - depth) to have retired, always a unit of w or older.
+        int pre = 0;   // units of the current segment staged during the previous segment
+        for (int w = 0; w < n_work; ++w, ++acc_it) {
+            const BmPairSeg sg = p.seg[seg_begin + w];
+            const int n_units = sg.unit_end - sg.unit_begin;
+            produce(it, pre, n_units);
             it += (uint32_t)n_units;
+            pre = 0;
+            if (kAhead > 0 && w + 1 < n_work) {
+                const BmPairSeg nx = p.seg[seg_begin + w + 1];
+                pre = min(kAhead, nx.unit_end - nx.unit_begin);
+                produce(it, 0, pre);
+            }
 #ifdef H2_BM_TRACE
             const long long pt_e0 = clock64();
 #endif
@@ -392,7 +416,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     const int row = j + rr;
                     float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + cc);
                     const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
-                    if (sg.role == kRoleSender) {
+                    if (sg.n_slots) {
                         float *dst = p.partial + ((int64_t)sg.slot * kTileRows + row0 + row) * (2 * FH) + fcol;
                         __stcg(reinterpret_cast<float4 *>(dst), v);
                     } else {
@@ -402,16 +426,15 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     }
                 }
             }
-            if (sg.role == kRoleSender) {
+            if (sg.n_slots) {
                 // ---- split item: publish the slot; the LAST CTA (of this rank) to arrive adds all slots and writes Y ----
                 constexpr int kEpiThreads = 32 * 4 * kPairGroups;
-                const BmPairFix fx = p.fix[sg.fix];
                 __threadfence();                               // this thread's slot stores, before the counter
                 named_bar_sync(1, kEpiThreads);
                 if (threadIdx.x == 0) {
                     uint32_t *cnt = p.sync + 2 * sg.fix + rank;
                     const uint32_t prev = atomicAdd(cnt, 1u);
-                    s_last = prev + 1 == (uint32_t)fx.n_slots;
+                    s_last = prev + 1 == (uint32_t)sg.n_slots;
                     if (s_last) { *cnt = 0; __threadfence(); }  // re-armed for the next launch; acquire side of the hand-over
                 }
                 named_bar_sync(1, kEpiThreads);
@@ -419,34 +442,41 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     constexpr int kLanes = 2 * FH / 4;         // float4 lanes per row: 32 (FH = 64) / 16 (FH = 32)
                     constexpr int kRowsPerWarp = 32 / kLanes;
                     const int sub_row = lane / kLanes, c = (lane % kLanes) * 4;
-                    const bool c_ok = fx.group * (2 * FH) + c + 4 <= p.d;
-                    // 4 rows per warp and pass: every slot load of a pass is issued before the first addition (a row at a
-                    // time serialised 16 L2 round trips per warp: +16 k cycles on the last CTA's critical path)
-                    constexpr int kU = 4;
+                    const bool c_ok = sg.group * (2 * FH) + c + 4 <= p.d;
+                    // kU rows per warp and pass, kS slots at a time: every load of a pass is in flight before the first
+                    // addition (r02 trace: one slot after the other cost n_slots L2 round trips per pass, ~12 k cycles on
+                    // the critical path of the CTA that finishes last); the additions keep the ascending slot order.
+                    constexpr int kU = 4, kS = 4;
                     const int r_lo = (int)rank * 128;
+                    const float *pbase = p.partial + (int64_t)sg.slot_begin * kTileRows * (2 * FH) + c;
                     for (int r0 = r_lo + (warp * kU) * kRowsPerWarp + sub_row; r0 < r_lo + 128; r0 += 8 * kU * kRowsPerWarp) {
                         float4 v[kU];
 #pragma unroll
-                        for (int i = 0; i < kU; ++i) {
-                            const int rr = r0 + i * kRowsPerWarp;
-                            v[i] = __ldcg(reinterpret_cast<const float4 *>(p.partial + ((int64_t)fx.slot_begin * kTileRows + rr) * (2 * FH) + c));
-                        }
-                        for (int k = 1; k < fx.n_slots; ++k) {   // ascending slot order: deterministic
-                            float4 t[kU];
+                        for (int i = 0; i < kU; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k0 = 0; k0 < sg.n_slots; k0 += kS) {
+                            float4 t[kS][kU];
 #pragma unroll
-                            for (int i = 0; i < kU; ++i) {
-                                const int rr = r0 + i * kRowsPerWarp;
-                                t[i] = __ldcg(reinterpret_cast<const float4 *>(p.partial + ((int64_t)(fx.slot_begin + k) * kTileRows + rr) * (2 * FH) + c));
+                            for (int k = 0; k < kS; ++k) {
+#pragma unroll
+                                for (int i = 0; i < kU; ++i) {
+                                    const int rr = r0 + i * kRowsPerWarp;
+                                    t[k][i] = k0 + k < sg.n_slots
+                                                  ? __ldcg(reinterpret_cast<const float4 *>(pbase + ((int64_t)(k0 + k) * kTileRows + rr) * (2 * FH)))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
                             }
 #pragma unroll
-                            for (int i = 0; i < kU; ++i) { v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w; }
+                            for (int k = 0; k < kS; ++k) {
+#pragma unroll
+                                for (int i = 0; i < kU; ++i) { v[i].x += t[k][i].x; v[i].y += t[k][i].y; v[i].z += t[k][i].z; v[i].w += t[k][i].w; }
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < kU; ++i) {
-                            const int64_t gr = (int64_t)fx.tile * kTileRows + r0 + i * kRowsPerWarp;
+                            const int64_t gr = (int64_t)sg.tile * kTileRows + r0 + i * kRowsPerWarp;
                             if (gr < p.n_rows && c_ok) {
                                 const float sc = xstep * (p.dinv_row ? p.dinv_row[gr] : 1.f);
-                                pair_store4(p.Y, gr * p.ldy + (int64_t)fx.group * (2 * FH) + c,
+                                pair_store4(p.Y, gr * p.ldy + (int64_t)sg.group * (2 * FH) + c,
                                             make_float4(v[i].x * sc, v[i].y * sc, v[i].z * sc, v[i].w * sc), p.y_bf16);
                             }
                         }
@@ -471,61 +501,109 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
 }
 
 // ---- host: stream-K schedule with roles ------------------------------------------------------------------------------
-// Work items (group, unit), group-major, are cut into `n_pairs` contiguous ranges of equal cost; a range is split at
-// (group, tile) boundaries and every kPairMaxSegUnits units.  Items covered by several segments get consecutive partial
-// slots (unit order = summation order) and an entry in the fix list the kernel's last phase works through.
+// Work items (group, unit), group-major, are cut into `n_pairs` contiguous ranges; a range is split at (group, tile)
+// boundaries and every kPairMaxSegUnits units.  Items covered by several segments get consecutive partial slots (unit
+// order = summation order) and an arrival counter.
+//
+// The ranges are cut at equal COST, not equal unit counts.  Costs in units of one MMA step (r02c trace, i8x3 d = 128: a
+// unit is ~384 cycles; an epilogue that writes Y ~5 k cycles; one that parks a partial slot, fences and bumps the
+// counter ~8 k; the ordered sum of the slots by whoever arrives last ~4 k, charged to the segment that holds the item's
+// FIRST units because its pair works on it last):
+//   cost(range) = units + sum over its segments of (whole ? kWhole : kSender) + kFix per split item whose head it holds
+// The smallest T for which a greedy left-to-right cut (every pair takes units while its cost stays <= T) needs at most
+// n_pairs ranges is found by scanning T upwards.  H2_PAIR_COSTS="whole,sender,fix" overrides the constants (measurement knob).
 void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int n_pairs_max, std::vector<BmPairSeg> &segs,
                    std::vector<int32_t> &pair_ptr, std::vector<BmPairFix> &fixes, int *n_slots_out) {
     const int64_t nt = (int64_t)tp.size() - 1, total = n_units * ng;
     const int G = (int)std::min<int64_t>(n_pairs_max, total);
     segs.clear();
+    fixes.clear();
     pair_ptr.assign(G + 1, 0);
-    constexpr int64_t kEpilogueUnits = 12;  // an epilogue (wait for the last MMAs, TMEM drain, conversion, write-out) ~ 6-7 k cycles (r02b trace) ~ 12 units of ~530
-    std::vector<int64_t> item_start;
-    for (int64_t grp = 0; grp < ng; ++grp)
-        for (int64_t t = 0; t < nt; ++t)
-            if (tp[t + 1] > tp[t]) item_start.push_back(grp * n_units + tp[t]);
-    auto cost_at = [&](int64_t q) {
-        return q + kEpilogueUnits * (int64_t)(std::lower_bound(item_start.begin(), item_start.end(), q) - item_start.begin());
+    *n_slots_out = 0;
+    if (G <= 0) return;
+    int64_t kWhole = 13, kSender = 21, kFix = 10;
+    if (const char *e = getenv("H2_PAIR_COSTS")) {
+        long a = 0, b = 0, c = 0;
+        if (sscanf(e, "%ld,%ld,%ld", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0) { kWhole = a; kSender = b; kFix = c; }
+    }
+    // end (in linear units) of the segment that starts at q: the item's end or the accumulator cut
+    auto seg_limit = [&](int64_t q, int64_t *item_begin, int64_t *item_end) {
+        const int64_t grp = q / n_units, u = q % n_units;
+        const int64_t t = (int64_t)(std::upper_bound(tp.begin(), tp.end(), u) - tp.begin()) - 1;   // tile of unit u
+        *item_begin = grp * n_units + tp[t];
+        *item_end = grp * n_units + tp[t + 1];
+        return std::min<int64_t>(*item_end, q + kPairMaxSegUnits);
     };
-    const int64_t cost_total = cost_at(total);
-    auto bound_for = [&](int c) {
-        if (c <= 0) return (int64_t)0;
-        if (c >= G) return total;
-        const int64_t target = cost_total * c / G;
-        int64_t lo = 0, hi = total;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (cost_at(mid) < target) lo = mid + 1; else hi = mid;
+    // greedy cut for a cost bound T: fills `bounds` (range ends) and returns the number of ranges used
+    auto cut = [&](int64_t T, std::vector<int64_t> *bounds) {
+        int used = 0;
+        int64_t q = 0;
+        while (q < total) {
+            int64_t cost = 0;
+            const int64_t q_start = q;
+            while (q < total) {
+                int64_t ib, ie;
+                const int64_t lim = seg_limit(q, &ib, &ie);
+                // entering a segment at q: if it runs to the end of its item AND starts at the item's begin it is whole
+                const bool at_begin = q == ib;
+                const int64_t fixed_whole = kWhole, fixed_split = kSender + (at_begin ? kFix : 0);
+                // take the whole remainder of the item if it fits as a whole / closing segment
+                const bool closes_item = lim == ie;
+                const int64_t full_cost = (lim - q) + ((at_begin && closes_item) ? fixed_whole : fixed_split);
+                if (cost + full_cost <= T) { cost += full_cost; q = lim; continue; }
+                // partial: as many units as fit next to the split epilogue (at least 1 if the range is still empty).
+                // A head or a tail shorter than the epilogue it costs is not worth a slot: the range rather ends at
+                // the item boundary, or leaves the next pair a tail of at least kMinPiece units.
+                int64_t room = T - cost - fixed_split;
+                const int64_t kMinPiece = 4;
+                if (q != q_start && room < (at_begin ? kMinPiece : 1)) break;
+                if (room < 1) room = 1;
+                int64_t take = std::min<int64_t>(room, lim - q);
+                if (closes_item && (lim - q) - take < kMinPiece && (lim - q) - take > 0)
+                    take = std::max<int64_t>(1, (lim - q) - kMinPiece);
+                q += take;
+                break;
+            }
+            ++used;
+            if (bounds) bounds->push_back(q);
         }
-        return lo;
+        return used;
     };
+    // smallest feasible T, scanning up from the perfect-balance bound in steps of 0.2 % (the greedy cut with its
+    // minimum-piece rules is not monotone in T, so no bisection)
+    int64_t lo = std::max<int64_t>(1, (total + kWhole * std::min<int64_t>(nt * ng, G)) / G);
+    const int64_t step = std::max<int64_t>(1, lo / 512);
+    while (cut(lo, nullptr) > G) lo += step;
+    std::vector<int64_t> bounds;
+    const int used = cut(lo, &bounds);
     for (int c = 0; c < G; ++c) {
-        const int64_t q0 = bound_for(c), q1 = bound_for(c + 1);
+        const int64_t q0 = c == 0 ? 0 : (c - 1 < used ? bounds[c - 1] : total), q1 = c < used ? bounds[c] : total;
         pair_ptr[c] = (int)segs.size();
         int64_t q = q0;
         while (q < q1) {
+            int64_t ib, ie;
+            const int64_t e = std::min<int64_t>(seg_limit(q, &ib, &ie), q1);
             const int64_t grp = q / n_units, u = q % n_units;
-            const int64_t t = (int64_t)(std::upper_bound(tp.begin(), tp.end(), u) - tp.begin()) - 1;   // tile of unit u
-            const int64_t e = std::min<int64_t>({tp[t + 1], n_units, u + (q1 - q), u + kPairMaxSegUnits});
-            segs.push_back(BmPairSeg{(int32_t)t, (int32_t)u, (int32_t)e, (int32_t)grp, kRoleWhole, 0, 0, 0});
-            q += e - u;
+            const int64_t t = (int64_t)(std::upper_bound(tp.begin(), tp.end(), u) - tp.begin()) - 1;
+            segs.push_back(BmPairSeg{(int32_t)t, (int32_t)u, (int32_t)(u + (e - q)), (int32_t)grp, 0, 0, 0, 0});
+            q = e;
         }
     }
     pair_ptr[G] = (int)segs.size();
-    // roles: segments of one item are consecutive in `segs` (unit order); split items get consecutive slots + a fix entry
+    // split items: segments of one item are consecutive in `segs` (unit order); they get consecutive slots + a counter
     int n_slots = 0;
-    fixes.clear();
     for (size_t i = 0; i < segs.size();) {
         size_t j = i + 1;
         while (j < segs.size() && segs[j].tile == segs[i].tile && segs[j].group == segs[i].group) ++j;
         if (j - i > 1) {
             fixes.push_back(BmPairFix{segs[i].tile, segs[i].group, n_slots, (int32_t)(j - i)});
             for (size_t k = i; k < j; ++k) {
-                segs[k].role = kRoleSender;
-                segs[k].slot = n_slots++;
+                segs[k].n_slots = (int32_t)(j - i);
+                segs[k].slot_begin = n_slots;
+                segs[k].slot = n_slots + (int32_t)(k - i);
                 segs[k].fix = (int32_t)fixes.size() - 1;
             }
+            n_slots += (int32_t)(j - i);
         }
         i = j;
     }

@@ -52,12 +52,18 @@ struct RoundParams {
     int32_t x_bf16, y_bf16;   // BASELINE config 5: bf16 features in / out, fp32 accumulation
 };
 
-// 4 consecutive features of a row: one 16-byte fp32 load, or one 8-byte load of 4 bf16 widened to fp32
-__device__ __forceinline__ float4 load_x4(const float *row, int j, int bf16) {
-    if (!bf16) return __ldg(reinterpret_cast<const float4 *>(row) + j);
-    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(row) + j);
-    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
-                       __uint_as_float(u.y & 0xFFFF0000u));
+// 4 consecutive features of a row: one 16-byte fp32 load, or one 8-byte load of 4 bf16 widened to fp32.  The row type is
+// a COMPILE-TIME parameter: as a run-time flag inside the gather loop it cost a branch region per load (r02: 48 issued
+// instructions per stored entry, the kernel was issue-bound at 71 % — profiles/README.md r02c).
+template <bool XB>
+__device__ __forceinline__ float4 load_x4(const char *p) {
+    if constexpr (!XB) {
+        return __ldg(reinterpret_cast<const float4 *>(p));
+    } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xFFFF0000u));
+    }
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
@@ -115,53 +121,79 @@ __global__ void plan_counts_kernel(const uint32_t *keys_sorted, int64_t n_vrows,
 }
 
 // ---- the fused round -------------------------------------------------------------------------------------------
-template <int LPR, int NV>
+// One batch step of accumulate_segment: G*U stored entries, U per lane group, all their X-row loads issued before the
+// first FMA.  FULL: the batch holds 32 entries and nothing is predicated.  Otherwise the entries past `cnt` re-load the
+// batch's last valid row (a row this output row reads anyway — no stray address, no select on the loaded values) and
+// only their FMAs are predicated off.  Lanes past the row width load column 0 instead (qoff) and never store.
+template <int LPR, int NV, int U, bool XB, bool FULL>
+__device__ __forceinline__ void gather_step(int t, int cnt, int c, float v, const char *xlane, int row_bytes, const int (&qoff)[NV],
+                                            int grp, float4 (&acc)[NV]) {
+    constexpr int G = 32 / LPR;
+    float4 x[U][NV];
+    float w[U];
+    bool on[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int idx = t + u * G + grp;            // < 32: G * U <= 32 and t is a multiple of G * U
+        on[u] = FULL || idx < cnt;
+        const int src = FULL ? idx : min(idx, cnt - 1);
+        const int cc = __shfl_sync(0xffffffffu, c, src);
+        w[u] = __shfl_sync(0xffffffffu, v, src);
+        const char *xr = xlane + (int64_t)cc * (int64_t)row_bytes;   // one IMAD.WIDE
+#pragma unroll
+        for (int q = 0; q < NV; ++q) x[u][q] = load_x4<XB>(xr + qoff[q]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (on[u]) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                acc[q].x = fmaf(w[u], x[u][q].x, acc[q].x);
+                acc[q].y = fmaf(w[u], x[u][q].y, acc[q].y);
+                acc[q].z = fmaf(w[u], x[u][q].z, acc[q].z);
+                acc[q].w = fmaf(w[u], x[u][q].w, acc[q].w);
+            }
+        }
+    }
+}
+
+// entries [s, e) of one CSR row: 32 (col, val) pairs per coalesced load, broadcast by shuffles; per entry the warp issues
+// 2 SHFL + 1 IMAD.WIDE + NV loads + 4 NV FFMA.  `xrow0` = row 0 of X (this hop's column slice), `row_bytes` the row
+// stride in bytes (< 2^31).
+template <int LPR, int NV, bool XB>
 __device__ __forceinline__ void accumulate_segment(const int32_t *__restrict__ col, const float *__restrict__ val,
                                                    const float *__restrict__ dinv, int64_t s, int64_t e,
-                                                   const float *__restrict__ X, int64_t ldx, int d4, int lane,
-                                                   float4 (&acc)[NV], int x_bf16) {
+                                                   const char *__restrict__ xrow0, int row_bytes, int d4, int lane,
+                                                   float4 (&acc)[NV]) {
     constexpr int G = 32 / LPR;             // nonzeros processed side by side
-    constexpr int U = (NV >= 4) ? 2 : ((NV == 2) ? 4 : 8);  // rows in flight per group
+    constexpr int U0 = (NV >= 4) ? 2 : ((NV == 2) ? 4 : 8);
+    constexpr int U = G * U0 > 32 ? 32 / G : U0;   // rows in flight per group
+    constexpr int kVec = XB ? 8 : 16;       // bytes of 4 features
     const int grp = lane / LPR;
     const int lig = lane % LPR;
-    for (int64_t base = s; base < e; base += 32) {
-        const int64_t k = base + lane;
+    const char *xlane = xrow0 + (lig < d4 ? lig * kVec : 0);
+    asm volatile("" : "+l"(xlane));         // keep the lane's base in a register pair (otherwise re-derived per load)
+    int qoff[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) qoff[q] = lig + q * LPR < d4 ? q * LPR * kVec : 0;
+    // 32-bit loop state: the row's entries as (pointer, count) — a row holds < 2^31 entries (RowDesc.len)
+    col += s;
+    if (val) val += s;
+    const int n = (int)(e - s);
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
         int c = 0;
         float v = 0.f;
-        if (k < e) {
+        if (k < n) {
             c = __ldg(col + k);
             v = val ? __ldg(val + k) : __ldg(dinv + c);
         }
-        const int cnt = (int)min((int64_t)32, e - base);
-        for (int t = 0; t < cnt; t += G * U) {
-            float4 x[U][NV];
-            float w[U];
+        if (n - base >= 32) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = t + u * G + grp;
-                const int cc = __shfl_sync(0xffffffffu, c, idx & 31);
-                const float vv = __shfl_sync(0xffffffffu, v, idx & 31);
-                const bool on = idx < cnt;
-                w[u] = on ? vv : 0.f;
-                // row start: ldx counts elements of the row type (2-byte elements: half the float stride)
-                const float *xr = x_bf16 ? reinterpret_cast<const float *>(reinterpret_cast<const uint16_t *>(X) + (int64_t)cc * ldx)
-                                         : X + (int64_t)cc * ldx;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int j = lig + q * LPR;
-                    x[u][q] = (on && j < d4) ? load_x4(xr, j, x_bf16) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    acc[q].x = fmaf(w[u], x[u][q].x, acc[q].x);
-                    acc[q].y = fmaf(w[u], x[u][q].y, acc[q].y);
-                    acc[q].z = fmaf(w[u], x[u][q].z, acc[q].z);
-                    acc[q].w = fmaf(w[u], x[u][q].w, acc[q].w);
-                }
-            }
+            for (int t = 0; t < 32; t += G * U) gather_step<LPR, NV, U, XB, true>(t, 32, c, v, xlane, row_bytes, qoff, grp, acc);
+        } else {
+            const int cnt = n - base;
+            for (int t = 0; t < cnt; t += G * U) gather_step<LPR, NV, U, XB, false>(t, cnt, c, v, xlane, row_bytes, qoff, grp, acc);
         }
     }
 }
@@ -192,7 +224,7 @@ __device__ __forceinline__ float4 epilogue(float4 a, float scale, const float *b
     return a;
 }
 
-template <int LPR, int NV>
+template <int LPR, int NV, bool XB>
 __global__ void __launch_bounds__(kCtaThreads, NV == 1 ? 4 : (NV == 2 ? 3 : 2))
 fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     extern __shared__ float4 s_part[];  // [kWarpsPerCta][d4] partial rows of a CTA-row
@@ -225,8 +257,9 @@ fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     float4 acc[NV];
 #pragma unroll
     for (int q = 0; q < NV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float *xbase = p.x_bf16 ? reinterpret_cast<const float *>(reinterpret_cast<const uint16_t *>(p.X) + hop.in_off) : p.X + hop.in_off;
-    accumulate_segment<LPR, NV>(hop.col, hop.val, hop.dinv, s, e, xbase, p.ldx, p.d4, lane, acc, p.x_bf16);
+    constexpr int kElt = XB ? 2 : 4;   // bytes per feature of an X row; ldx and the in offsets count elements of the row type
+    const char *xrow0 = reinterpret_cast<const char *>(p.X) + hop.in_off * kElt;
+    accumulate_segment<LPR, NV, XB>(hop.col, hop.val, hop.dinv, s, e, xrow0, (int)(p.ldx * kElt), p.d4, lane, acc);
     reduce_groups<LPR, NV>(acc);
 
     const float scale = hop.val ? 1.f : __ldg(hop.dinv_row + i);  // factored mode: dinv_i * sum_j dinv_j x_j
@@ -262,8 +295,8 @@ fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     }
 }
 
-template <int LPR, int NV>
-static int launch_gather(const RoundParams &p, cudaStream_t st) {
+template <int LPR, int NV, bool XB>
+static int launch_gather_t(const RoundParams &p, cudaStream_t st) {
     const int64_t warp_rows = p.n_vrows - p.n_cta_rows;
     const int64_t grid = p.n_cta_rows + (warp_rows + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid == 0) return H2_OK;
@@ -271,9 +304,15 @@ static int launch_gather(const RoundParams &p, cudaStream_t st) {
     // the partial rows are only needed by CTA-rows; without them the CTA takes no shared memory and fits next to the
     // persistent tensor-core CTA of the same round
     const size_t smem = p.n_cta_rows ? (size_t)kWarpsPerCta * p.d4 * sizeof(float4) : 0;
-    fused_hops_gather_kernel<LPR, NV><<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
+    fused_hops_gather_kernel<LPR, NV, XB><<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
     H2_LAUNCHED("fused_hops_gather_kernel");
     return H2_OK;
+}
+
+template <int LPR, int NV>
+static int launch_gather(const RoundParams &p, cudaStream_t st) {
+    H2_REQUIRE(p.ldx * 4 < (1ll << 31), H2_ERR_UNSUPPORTED, "fused round: ldx=%lld is too wide (row stride must stay below 2 GiB)", (long long)p.ldx);
+    return p.x_bf16 ? launch_gather_t<LPR, NV, true>(p, st) : launch_gather_t<LPR, NV, false>(p, st);
 }
 
 int run_gather_round(const RoundParams &p, cudaStream_t st) {
