@@ -814,7 +814,9 @@ static int groups_for(int d, int dg) { int g = (d + dg - 1) / dg, p2 = 1; while 
 static int groups_for_splits(int d, int dg, int splits) { const int g = groups_for(d, dg); return splits_i8(splits) ? std::max(2, g) : g; }
 // features per packed B tile: 32 for 3 bf16 pieces and narrow rounds; int8 rounds use 32 up to d = 64 (the two halves of
 // the pair kernel's 64-feature group) and 64 above
-static int dg_for(int d, int splits) { return (d <= 32 || splits == 3 || (splits_i8(splits) && d <= 64)) ? 32 : 64; }
+// (H2_BM_FH32_UPTO = widest int8 round that still uses 32-feature tiles: measurement knob, default 64)
+static int i8_fh32_upto() { static const int v = [] { const char *e = getenv("H2_BM_FH32_UPTO"); return e ? atoi(e) : 64; }(); return v; }
+static int dg_for(int d, int splits) { return (d <= 32 || splits == 3 || (splits_i8(splits) && d <= i8_fh32_upto())) ? 32 : 64; }
 static size_t i8_tile_bytes(int dg, int splits) { return (size_t)splits_pieces(splits) * dg * 64 + kI8ConstBytes; }
 struct I8Layout {   // int8 xpack buffer: header | tiles | rowmax [n_slabs][n_cols] | blockmax [kPackMaxCtas]
     int64_t n_chunks, n_groups, n_slabs;
@@ -853,7 +855,7 @@ static size_t pair_sched_bytes(int64_t nt, int64_t n_units, int ng) {
 // every int8 round runs on the pair kernel: FH = 32 (d <= 64; a round of <= 32 features computes a zero-padded second
 // half) or FH = 64 features per CTA half, 1 / 2 / 4 column groups of 2*FH features
 static bool pair_applies(int32_t splits, int d) { return splits_i8(splits) && d > 0; }
-static int pair_fh(int d) { return d <= 64 ? 32 : 64; }
+static int pair_fh(int d) { return d <= i8_fh32_upto() ? 32 : 64; }
 static int pair_groups(int d) { return std::max(2, groups_for(d, pair_fh(d))) / 2; }
 
 }  // namespace h2

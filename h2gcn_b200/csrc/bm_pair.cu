@@ -42,7 +42,8 @@ constexpr int kPairMaxSegUnits = 2048;                      // int32 accumulator
 
 struct BmPairSeg {        // one contiguous run of units inside one (row tile, column group), handled by one CTA pair
     int32_t tile, unit_begin, unit_end, group;
-    int32_t n_slots;      // 0: the segment covers its whole item and writes Y; else the item is split into n_slots segments
+    int32_t n_slots;      // 0: the segment covers its whole item and writes Y; else the item is split into |n_slots| segments
+                          // (negative: this segment is the designated finisher of the item, see the epilogue)
     int32_t slot;         // split item: this segment's partial slot (slots of an item are consecutive, unit order)
     int32_t fix;          // split item: index of the item (arrival counters)
     int32_t slot_begin;   // split item: first slot of the item
@@ -164,6 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_chunk[32];
     __shared__ bool s_last;
+    __shared__ bool s_fast[2];
     uint32_t bar0 = smem_u32(&s_bar[0]);
     asm volatile("" : "+r"(bar0));
     const uint32_t bar_full_a = bar0;                                  // leader only: 8 producer warps (4 of each CTA)
@@ -367,12 +369,26 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
             float *s_scale = stage + 32;                            // staged rows have 4 spare floats each: row r's scale at [r * 36 + 32]
             mbar_wait(bar_acc_full, acc_it & 1);
             tc_fence_after();
+            // Split item, DESIGNATED finisher (n_slots < 0: the segment the schedule expects to end last, always the last
+            // one of its pair): after staging its first block it waits — bounded — until the other segments have
+            // published their slots, then the write-out below adds them to the staged values in slot order and stores Y:
+            // no slot store, no fence, no counter round trip, no separate pass over the slots (r02d trace: that pass
+            // cost ~9 k cycles at the very end of the pair that arrived last).  If the patience runs out the segment
+            // publishes its slot like the others and whoever arrives last sums them (below): nobody waits for long,
+            // no co-residency assumption.
+            constexpr int kFastMaxSlots = 4;
+            constexpr long long kFinisherPatience = 24000;          // cycles
+            const int n_slots = sg.n_slots < 0 ? -sg.n_slots : sg.n_slots;
+            const bool designated = sg.n_slots < 0 && n_slots <= kFastMaxSlots && w + 1 == n_work;
+            bool fast = false;
+            const int own_pos = sg.slot - sg.slot_begin;
             constexpr int kRowsPerInstr = 4;                        // 8 lanes x float4 = one 32-float row segment
             const int rr = lane >> 3, cc = (lane & 7) * 4;
             const int row0 = (int)rank * 128 + quarter * 32;        // first row (inside the 256-row tile) of this warp
             const float scale_row = xstep * ((grow < p.n_rows && p.dinv_row) ? p.dinv_row[grow] : 1.f);
-#pragma unroll 1
-            for (int c0 = 0; c0 < FH; c0 += 32) {
+
+            // accumulator block c0 (32 features of this warp's half) -> fp32 -> stage buffer `stg` (lane = row)
+            auto drain = [&](int c0, float *stg) {
                 __syncwarp();                   // the stage is free (previous block / segment written out)
                 if (c0 == 0) s_scale[lane * kStageStride] = scale_row;
 #pragma unroll
@@ -404,17 +420,63 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                             for (int s = S - 2; s >= 0; --s, wgt *= 256.f) v = fmaf((float)(int32_t)acc[s][q + e], wgt, v);
                             po[e] = v;
                         }
-                        *reinterpret_cast<float4 *>(stage + lane * kStageStride + 16 * hb + q) = o;
+                        *reinterpret_cast<float4 *>(stg + lane * kStageStride + 16 * hb + q) = o;
                     }
                 }
                 __syncwarp();
-                // coalesced write-out: an instruction covers 4 rows x 32 floats
+            };
+            // coalesced write-out of a staged block: an instruction covers 4 rows x 32 floats.  fast: + the other slots, -> Y;
+            // split item: -> this segment's partial slot; whole item: -> Y
+            auto write_out = [&](int c0, const float *stg) {
                 const int fcol = sub * FH + c0 + cc;                               // column inside the 2*FH-wide group
                 const bool col_ok = f_base + c0 + cc + 4 <= p.d;
+                if (fast) {
+                    // the (at most 3) other slots in ascending order around the own one; with one or two of them all 8 row
+                    // instructions of the block are loaded in ONE pass (every load in flight before the first sum: one L2
+                    // round trip per block instead of two), with three in two passes
+                    const float *pb = p.partial + ((int64_t)sg.slot_begin * kTileRows + row0 + rr) * (2 * FH) + fcol;
+                    auto finish_rows = [&](auto n_others_c, auto rows_c, int jh) {
+                        constexpr int NO = decltype(n_others_c)::value, NR = decltype(rows_c)::value;
+                        float4 t[NO][NR];
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) {
+                            const int k = o < own_pos ? o : o + 1;     // slot index of the o-th other slot
+#pragma unroll
+                            for (int i = 0; i < NR; ++i)
+                                t[o][i] = k < n_slots ? __ldcg(reinterpret_cast<const float4 *>(pb + ((int64_t)k * kTileRows + jh + i * kRowsPerInstr) * (2 * FH)))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int row = jh + i * kRowsPerInstr + rr;
+                            const float4 own = *reinterpret_cast<const float4 *>(stg + row * kStageStride + cc);
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int k = 0; k <= NO; ++k) {            // ascending slot order, the own slot at its place
+                                if (k < n_slots) {   // compile-time indices only (a run-time index would put t[] in local memory)
+                                    const float4 lo = t[k < NO ? k : NO - 1][i], hi = t[k > 0 ? k - 1 : 0][i];
+                                    const float4 a = k == own_pos ? own : (k < own_pos ? lo : hi);
+                                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                                }
+                            }
+                            const float sc = s_scale[row * kStageStride];
+                            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                            const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
+                            if (col_ok && gr < p.n_rows) pair_store4(p.Y, gr * p.ldy + (int64_t)sg.group * (2 * FH) + fcol, v, p.y_bf16);
+                        }
+                    };
+                    if (n_slots <= 3) {
+                        finish_rows(std::integral_constant<int, 2>{}, std::integral_constant<int, 8>{}, 0);
+                    } else {
+                        finish_rows(std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{}, 0);
+                        finish_rows(std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{}, 4 * kRowsPerInstr);
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += kRowsPerInstr) {
                     const int row = j + rr;
-                    float4 v = *reinterpret_cast<const float4 *>(stage + row * kStageStride + cc);
+                    float4 v = *reinterpret_cast<const float4 *>(stg + row * kStageStride + cc);
                     const int64_t gr = (int64_t)sg.tile * kTileRows + row0 + row;
                     if (sg.n_slots) {
                         float *dst = p.partial + ((int64_t)sg.slot * kTileRows + row0 + row) * (2 * FH) + fcol;
@@ -425,8 +487,37 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                         if (col_ok && gr < p.n_rows) pair_store4(p.Y, gr * p.ldy + (int64_t)sg.group * (2 * FH) + fcol, v, p.y_bf16);
                     }
                 }
+            };
+            if (designated) {
+                // the pair's LAST segment: every MMA has completed and every TMA copy has been consumed, so the B ring is
+                // free — its first bytes stage the second block, and ALL accumulators are drained before the wait
+                float *stage2 = reinterpret_cast<float *>(smem_raw + (smem_base - smem_raw_u32)) + warp * (32 * kStageStride);
+                static_assert(8 * 32 * Cfg::kStageStride * 4 <= Cfg::kBStg * Cfg::kBStride && FH <= 64, "second stage inside the B ring");
+#pragma unroll 1
+                for (int c0 = 0; c0 < FH; c0 += 32) drain(c0, c0 == 0 ? stage : stage2);
+                if (threadIdx.x == 0) {
+                    const int32_t *cnt = reinterpret_cast<const int32_t *>(p.sync + 2 * sg.fix + rank);
+                    const long long t0 = clock64();
+                    bool f = ld_acquire_gpu(cnt) == n_slots - 1;
+                    while (!f && clock64() - t0 < kFinisherPatience) {
+                        __nanosleep(64);
+                        f = ld_acquire_gpu(cnt) == n_slots - 1;
+                    }
+                    if (f) p.sync[2 * sg.fix + rank] = 0;       // nobody else arrives any more: re-armed for the next launch
+                    s_fast[acc_it & 1] = f;
+                }
+                named_bar_sync(1, 32 * 4 * kPairGroups);
+                fast = s_fast[acc_it & 1];
+#pragma unroll 1
+                for (int c0 = 0; c0 < FH; c0 += 32) write_out(c0, c0 == 0 ? stage : stage2);
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < FH; c0 += 32) {
+                    drain(c0, stage);
+                    write_out(c0, stage);
+                }
             }
-            if (sg.n_slots) {
+            if (sg.n_slots && !fast) {
                 // ---- split item: publish the slot; the LAST CTA (of this rank) to arrive adds all slots and writes Y ----
                 constexpr int kEpiThreads = 32 * 4 * kPairGroups;
                 __threadfence();                               // this thread's slot stores, before the counter
@@ -434,7 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                 if (threadIdx.x == 0) {
                     uint32_t *cnt = p.sync + 2 * sg.fix + rank;
                     const uint32_t prev = atomicAdd(cnt, 1u);
-                    s_last = prev + 1 == (uint32_t)sg.n_slots;
+                    s_last = prev + 1 == (uint32_t)n_slots;
                     if (s_last) { *cnt = 0; __threadfence(); }  // re-armed for the next launch; acquire side of the hand-over
                 }
                 named_bar_sync(1, kEpiThreads);
@@ -453,14 +544,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                         float4 v[kU];
 #pragma unroll
                         for (int i = 0; i < kU; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int k0 = 0; k0 < sg.n_slots; k0 += kS) {
+                        for (int k0 = 0; k0 < n_slots; k0 += kS) {
                             float4 t[kS][kU];
 #pragma unroll
                             for (int k = 0; k < kS; ++k) {
 #pragma unroll
                                 for (int i = 0; i < kU; ++i) {
                                     const int rr = r0 + i * kRowsPerWarp;
-                                    t[k][i] = k0 + k < sg.n_slots
+                                    t[k][i] = k0 + k < n_slots
                                                   ? __ldcg(reinterpret_cast<const float4 *>(pbase + ((int64_t)(k0 + k) * kTileRows + rr) * (2 * FH)))
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                                 }
@@ -505,13 +596,16 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
 // boundaries and every kPairMaxSegUnits units.  Items covered by several segments get consecutive partial slots (unit
 // order = summation order) and an arrival counter.
 //
-// The ranges are cut at equal COST, not equal unit counts.  Costs in units of one MMA step (r02c trace, i8x3 d = 128: a
-// unit is ~384 cycles; an epilogue that writes Y ~5 k cycles; one that parks a partial slot, fences and bumps the
-// counter ~8 k; the ordered sum of the slots by whoever arrives last ~4 k, charged to the segment that holds the item's
-// FIRST units because its pair works on it last):
+// The ranges are cut at equal COST, not equal unit counts.  Costs in units of one MMA step, calibrated on the per-pair
+// traces of the north-star round (i8x3, d = 128: a unit is ~384 cycles; profiles/README.md r02c): a pair with one
+// segment spends ~11 k cycles outside its MMAs (start-up 3.4 k, last epilogue 7.7 k), every further segment ~8 k more
+// (accumulator drain with the tensor pipe idle, slot store, fence, counter, refill): kSender ~ 24 per split segment,
+// kWhole ~ 10 for a segment that writes Y itself; kFix = extra charge for the segment holding an item's first units
+// (0 since the designated finisher adds the slots inside its own write-out):
 //   cost(range) = units + sum over its segments of (whole ? kWhole : kSender) + kFix per split item whose head it holds
 // The smallest T for which a greedy left-to-right cut (every pair takes units while its cost stays <= T) needs at most
-// n_pairs ranges is found by scanning T upwards.  H2_PAIR_COSTS="whole,sender,fix" overrides the constants (measurement knob).
+// n_pairs ranges is found by scanning T upwards.  H2_PAIR_COSTS="whole,sender,fix" overrides the constants (measurement
+// knob; measured: 38.0-38.1 us per pipelined tensor hop for 13,21,0 / 10,24,0 / 13,27,0, 39.1 for 8,12,6).
 void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int n_pairs_max, std::vector<BmPairSeg> &segs,
                    std::vector<int32_t> &pair_ptr, std::vector<BmPairFix> &fixes, int *n_slots_out) {
     const int64_t nt = (int64_t)tp.size() - 1, total = n_units * ng;
@@ -521,7 +615,7 @@ void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int 
     pair_ptr.assign(G + 1, 0);
     *n_slots_out = 0;
     if (G <= 0) return;
-    int64_t kWhole = 13, kSender = 21, kFix = 10;
+    int64_t kWhole = 10, kSender = 24, kFix = 0;
     if (const char *e = getenv("H2_PAIR_COSTS")) {
         long a = 0, b = 0, c = 0;
         if (sscanf(e, "%ld,%ld,%ld", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0) { kWhole = a; kSender = b; kFix = c; }
@@ -607,6 +701,30 @@ void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int 
         }
         i = j;
     }
+    // designated finisher of every split item: the segment expected to END last (estimated finish time inside its pair),
+    // provided it is the last segment of its pair (a finisher may wait for its mates; nothing may queue behind it)
+    std::vector<int64_t> finish(segs.size(), 0);
+    std::vector<char> last_of_pair(segs.size(), 0);
+    for (int c = 0; c < G; ++c) {
+        int64_t t = 0;
+        for (int i = pair_ptr[c]; i < pair_ptr[c + 1]; ++i) {
+            t += (segs[i].unit_end - segs[i].unit_begin) + (segs[i].n_slots ? kSender : kWhole);
+            finish[i] = t;
+        }
+        if (pair_ptr[c + 1] > pair_ptr[c]) last_of_pair[pair_ptr[c + 1] - 1] = 1;
+    }
+    if (!getenv("H2_PAIR_NO_FINISHER"))
+        for (size_t i = 0; i < segs.size();) {
+            size_t j = i + 1;
+            while (j < segs.size() && segs[j].tile == segs[i].tile && segs[j].group == segs[i].group) ++j;
+            if (j - i > 1) {
+                size_t best = i;
+                for (size_t k = i + 1; k < j; ++k)
+                    if (finish[k] >= finish[best]) best = k;
+                if (last_of_pair[best]) segs[best].n_slots = -segs[best].n_slots;
+            }
+            i = j;
+        }
     *n_slots_out = n_slots;
 }
 

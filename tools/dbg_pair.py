@@ -34,10 +34,23 @@ for k, nm in enumerate(names):
 for c in (0, 1, 2, 3, 72, 73, 146, 147):
     print("cta", c, "dur", int(dur[c]), [int(v) for v in b[c, 2:12]])
 
+if os.environ.get("H2_TRACE_DUMP"):
+    np.savetxt(os.environ["H2_TRACE_DUMP"], np.concatenate([dur[:, None], b[:, 2:12]], axis=1), fmt="%d", delimiter=",",
+               header="dur,mma_wait_full_a,mma_wait_acc_empty,prod_wait_full_b,prod_wait_empty_a,prod_expand_store,tma_wait_empty_b,epilogue_w0,recv_spin,units,segments")
+# per pair: duration (max of its two CTAs), units, segments -> least-squares  dur ~ a + b * units + c * (segments - 1)
+pd = np.maximum(dur[0::2], dur[1::2]).astype(np.float64)
+pu, ps = lead[:, 10].astype(np.float64), lead[:, 11].astype(np.float64)
+ok = pu > 0
+A = np.stack([np.ones(ok.sum()), pu[ok], ps[ok] - 1], axis=1)
+coef, *_ = np.linalg.lstsq(A, pd[ok], rcond=None)
+print("fit: dur = %.0f + %.1f * units + %.0f * (segments - 1);  residual rms %.0f" % (coef[0], coef[1], coef[2], np.sqrt(np.mean((A @ coef - pd[ok]) ** 2))))
+for sgs in (1, 2, 3):
+    m = ok & (ps == sgs)
+    if m.any(): print("pairs with %d segment(s): n %d  units mean %.1f  dur mean %.0f min %.0f max %.0f  epilogue(w0 of leader) mean %.0f" % (sgs, m.sum(), pu[m].mean(), pd[m].mean(), pd[m].min(), pd[m].max(), lead[m, 8].mean()))
 u = np.zeros(8 * 96, dtype=np.int64)
 lib.h2_debug_read_pair_units(u.ctypes.data_as(ctypes.c_void_p))
 u = u.reshape(8, 96) - b[0, 0]
 names = ["TMA issued", "B landed", "expanded", "A free", "stored", "MMA saw A", "MMA issued"]
 print("unit " + " | ".join(n.rjust(10) for n in names))
-for k in range(60):
+for k in range(int(os.environ.get("H2_TRACE_UNITS", "6"))):
     print("%4d " % k + " | ".join(("%10d" % u[r, k]) if u[r, k] > 0 else " " * 10 for r in range(7)))
