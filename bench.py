@@ -31,6 +31,10 @@ E_PER_GPU = 200_000
 FEAT = 128
 RMAT_N = int(os.environ.get("H2_BENCH_RMAT_N", 1 << 20))           # BASELINE config 4 (override only for dry runs)
 RMAT_E = int(os.environ.get("H2_BENCH_RMAT_E", 16 * (1 << 20)))
+CFG5_N = int(os.environ.get("H2_BENCH_CFG5_N", 4 << 20))           # BASELINE config 5 (override for smaller boxes / dry runs)
+CFG5_E = int(os.environ.get("H2_BENCH_CFG5_E", 64 << 20))
+CFG5_FEAT = int(os.environ.get("H2_BENCH_CFG5_FEAT", 256))
+CFG5_GAMMA = 2.5
 L2_FLUSH_BYTES = 256 << 20
 L2_BYTES = 126 << 20
 DEFAULT_SPLITS = None      # arithmetic of the tensor-core path: None = the library default (i8x3, fp32-equivalent)
@@ -385,7 +389,9 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="N>1: hop-boundary exchange (p2p = fused into the pack kernel over peer memory)")
     ap.add_argument("--splits", default=DEFAULT_SPLITS, help="arithmetic of the tensor-core path: i8x3 (default: 3 int8 digits + row "
                     "exponents, fp32-equivalent) | i8x2 | 2 | 3 (bf16 pieces)")
-    ap.add_argument("--workload", default="auto", choices=["auto", "uniform"], help="N>1: auto = R-MAT config 4, uniform = the weak-scaling uniform graph of round 1")
+    ap.add_argument("--workload", default="auto", choices=["auto", "uniform", "cfg5"],
+                    help="N>1: auto = R-MAT config 4, uniform = the weak-scaling uniform graph of round 1; cfg5 (any N) = BASELINE config 5: "
+                         "power-law |V|=4M |E|=64M d=256, bf16 feature rows in / out")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: anything a library writes to fd 1 (NCCL prints its version banner there
     # when NCCL_DEBUG is set) is sent to stderr instead
@@ -400,6 +406,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 through torchrun)"
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    if args.workload == "cfg5":
+        return main_cfg5(args)
     if world == 1:
         return main_single(args)
     return main_multi(args)
@@ -781,6 +789,164 @@ def main_multi(args):
     _JSON_OUT.write(json.dumps(line) + "\n")
     _JSON_OUT.flush()
     dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: power-law |V| = 4M, 64M edge draws, d = 256, bf16 feature rows, rows sharded over the GPUs
+# ----------------------------------------------------------------------------------------------------------------------
+def main_cfg5(args):
+    """2-hop precompute + fused round on the power-law graph with bf16 rows (X shards, gathered copy and Y in bf16, fp32
+    accumulation).  One line: precompute seconds, round time, parity of a row sample against the oracle on the host."""
+    import torch
+    import torch.distributed as dist
+    from h2gcn_b200 import _cabi
+    from h2gcn_b200.parallel import ShardedGraph
+    from h2gcn_b200.utils import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+    n, n_edges, d = CFG5_N, CFG5_E, CFG5_FEAT
+    desc = (f"power-law (Chung-Lu, exponent {CFG5_GAMMA}) |V|={n} {n_edges} edge draws (symmetrised, deduplicated, no self loops) "
+            f"d={d} bf16 feature rows in / out, seed 2, rows sharded over the GPUs (BASELINE config 5)")
+    t0 = time.perf_counter()
+    adj = synth.chung_lu_graph_device(n, n_edges, gamma=CFG5_GAMMA, seed=2, device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = ShardedGraph(adj, rank, world, dev, factored=True, mode=args.mode, splits=args.splits, exchange=args.exchange,
+                     explicit_vals=False, balance="auto")
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1005)
+    x_all = torch.randn(n, d, device=dev, generator=gen).to(torch.bfloat16)          # the same matrix on every rank
+    x_local = x_all[g.row_begin:g.row_end].contiguous()
+    if world > 1 and g.exchange == "p2p":
+        buf = g.input_buffer(d, torch.bfloat16)
+        buf.copy_(x_local)
+        x_local = buf
+    x_host = x_all.float().cpu().numpy() if rank == 0 and not args.no_cpu_baseline else None
+    del x_all
+    torch.cuda.empty_cache()
+    y = torch.empty(g.n_local, 2 * d, device=dev, dtype=torch.bfloat16)
+
+    def step():
+        g.round(x_local, y, [0, d])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    torch.cuda.synchronize()
+    barrier()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.finish()
+    barrier()
+    my_ms = float(ev0.elapsed_time(ev1))
+    tt = torch.tensor([my_ms], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([g.nnz_local, g.nnz2_local], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt)
+    total_ms = float(tt.item())
+    nnz_total, nnz2_total = int(cnt[0].item()), int(cnt[1].item())
+    ms_per_step = total_ms / args.steps
+    value = nnz_total * d / (ms_per_step * 1e-3)
+
+    # e2e: the rank's rows of X from pinned host memory, its rows of Y back
+    xh = x_local.cpu().pin_memory()
+    yh = torch.empty(g.n_local, 2 * d, dtype=torch.bfloat16).pin_memory()
+    k_e2e = min(args.steps, 5)
+    for _ in range(1):
+        x_local.copy_(xh, non_blocking=True); step(); yh.copy_(y, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        x_local.copy_(xh, non_blocking=True); step(); yh.copy_(y, non_blocking=True)
+        torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / k_e2e
+
+    parity = None
+    if rank == 0 and x_host is not None:
+        from oracle import cbind
+        rng = np.random.default_rng(11)
+        deg_all = g.deg2_host
+        live = np.nonzero(deg_all[g.row_begin:g.row_end] > 0)[0]
+        pick = np.sort(rng.choice(live, size=min(64, len(live)), replace=False)) if len(live) else np.arange(min(64, g.n_local))
+        rows = pick + g.row_begin
+        (rp1, c1, v1), (rp2, c2, v2) = sample_hops_cpu(adj, rows, deg_all)
+        ref = cbind.fused_round(rp1, c1, v1, rp2, c2, v2, x_host, threads=host_threads())
+        got = y[torch.from_numpy(pick).to(dev)].float().cpu().numpy()
+        parity = parity_metrics(got, ref)
+        err = np.abs(got.astype(np.float64) - ref)
+        parity.update({"tolerance": 2.0 ** -8, "tolerance_note": "bf16 output: every element within one bf16 rounding (2^-8 relative) of the "
+                       "oracle's fp32 result on the same bf16 inputs, + 1e-5 of the max for cancelled sums",
+                       "within_one_bf16_rounding": bool((err <= 2.0 ** -8 * np.abs(ref) + 1e-5 * np.abs(ref).max()).all()),
+                       "against": "oracle C port on the host (in-order fp32 sums) on the bf16-rounded inputs; 2-hop rows rebuilt from the definition with scipy",
+                       "rows_checked": int(len(rows)), "entries_checked": int(len(c1) + len(c2)),
+                       "deg2_of_sample_matches_gpu": bool(np.array_equal(np.diff(rp2), deg_all[rows]))})
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    # compulsory bytes of rank 0's shard, bf16 rows: factored CSR (4 B per entry) + X (2 B) + Y (2 x 2 B)
+    balg = 2 * (g.n_local + 1) * 8 + g.nnz_local * 4 + n * d * 2 + 2 * g.n_local * d * 2
+    kern_ms = my_ms / args.steps
+    achieved = balg / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges*featdim/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 rows, f32 accumulation" + ("" if not g.plan.tensor_idx else " / i8 digits"), "data": "synthetic",
+        "config": {"workload": desc, "exchange": g.exchange, "n_vertices": n, "n_edge_draws": n_edges, "nnz1": g.nnz1_global,
+                   "nnz2": nnz2_total, "nnz_total": nnz_total, "nnz_local_rank0": g.nnz_local, "rows_rank0": g.n_local,
+                   "max_degree": g.max_deg1, "max_degree_2hop": g.max_deg2, "zero_degree_rows": g.zero_deg1,
+                   "row_partition": g.balance, "adjacency_values": "factored (dinv_i * dinv_j over the binary pattern)",
+                   "kernel": g.plan.kernel_name, "graph_generation_s": t_gen,
+                   "precompute_s": t_pre, "precompute_what": "per rank: 2-hop degree count (equal-rows split, all-gathered), hop2 fill + "
+                   "SYM normalisation of its rows, round plan; host wall clock",
+                   "precompute_nnz2_per_s": nnz2_total / t_pre, "wall_s_timed_region": wall, "parity": parity,
+                   "l2": "inputs larger than L2 (the rank's hop pattern alone is gigabytes); K steps between ONE CUDA-event pair, max over ranks"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "kernel_ms": kern_ms,
+                     "note": "rank 0: compulsory bytes of its shard's round (factored CSR indices, bf16 X and Y) / its mean round time, "
+                             "against ONE GPU's measured HBM bandwidth"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": nnz_total * d / e2e_s, "unit": "edges*featdim/s", "h2d_bytes_per_step": int(g.n_local * d * 2),
+                "d2h_bytes_per_step": int(g.n_local * 2 * d * 2), "ms_per_step": 1e3 * e2e_s, "steps": k_e2e,
+                "api": "per rank: its bf16 rows of X from pinned host memory -> ShardedGraph.round (h2_graph_round_parts_ex) -> its bf16 rows "
+                       "of Y to pinned host memory, synchronise; host wall clock, max over ranks"},
+    }
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -102,6 +102,8 @@ PROTOTYPES = {
     "h2_graph_round_multi": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
     "h2_graph_round_parts": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i64, c_vp, c_i64,
                                             c_vp, c_i64, ctypes.POINTER(c_i64), c_vp]),
+    "h2_graph_round_parts_ex": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i64, c_i32, c_vp, c_i64,
+                                               c_vp, c_i64, c_i32, ctypes.POINTER(c_i64), c_vp]),
     "h2_sum_slices_f32": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "h2_graph_destroy": (ctypes.c_int, [c_vp]),
 }

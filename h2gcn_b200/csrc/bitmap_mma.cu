@@ -171,6 +171,22 @@ __global__ void gather_rows_kernel(int32_t n_cols, int32_t d4, const __grid_cons
     reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full)[c] = reinterpret_cast<const float4 *>(pack_src_row(src, j))[c];
 }
 
+// the gathered copy of a row-sharded input keeps the row type of the shards (fp32, or bf16 with ld_full counting bf16
+// elements): element offset `off`, 4 consecutive features
+__device__ __forceinline__ float4 xfull_load4(const float *xfull, int64_t off, int bf16) {
+    if (!bf16) return *reinterpret_cast<const float4 *>(xfull + off);
+    const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(xfull) + off);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ void xfull_store4(float *xfull, int64_t off, float4 v, int bf16) {
+    if (!bf16) { *reinterpret_cast<float4 *>(xfull + off) = v; return; }
+    // the values came from bf16 rows: the upper halves are the original bits (exact)
+    const uint32_t lo = (__float_as_uint(v.x) >> 16) | (__float_as_uint(v.y) & 0xFFFF0000u);
+    const uint32_t hi = (__float_as_uint(v.z) >> 16) | (__float_as_uint(v.w) & 0xFFFF0000u);
+    *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(xfull) + off) = make_uint2(lo, hi);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // int8 operand (kind::i8): X' = diag(dinv) X as block-fixed-point.
 //   x'[j][c] ~= step * 2^t(j) * q[j][c],   q an integer of S balanced base-256 digits (|q| <= i8_range(S)),
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(kPackThreads) bm_pack_i8_kernel(int32_t n_cols
             sc[i] = 0.f;
             if (j < n_cols && f0 + f4 < d) {   // d % 4 == 0: a float4 is either fully inside or fully outside
                 if (first_pass || !xfull) v[i] = pack_src_load4(src, pack_src_row(src, j), f0 + f4);   // plain load: may be peer memory
-                else v[i] = *reinterpret_cast<const float4 *>(xfull + (int64_t)j * ld_full + f0 + f4);   // second pass: the local copy
+                else v[i] = xfull_load4(xfull, (int64_t)j * ld_full + f0 + f4, src.bf16);                // second pass: the local copy
                 sc[i] = dinv ? __ldg(dinv + j) : 1.f;
             }
         }
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(kPackThreads) bm_pack_i8_kernel(int32_t n_cols
             const int k = idx / V, f4 = (idx % V) * 4;
             const int j = j0 + k;
             if (xfull && first_pass && j < n_cols && f0 + f4 < d)
-                *reinterpret_cast<float4 *>(xfull + (int64_t)j * ld_full + f0 + f4) = v[i];   // gathered fp32 copy
+                xfull_store4(xfull, (int64_t)j * ld_full + f0 + f4, v[i], src.bf16);          // gathered copy, in the row type
             s_x[k][f4] = v[i].x * sc[i]; s_x[k][f4 + 1] = v[i].y * sc[i]; s_x[k][f4 + 2] = v[i].z * sc[i]; s_x[k][f4 + 3] = v[i].w * sc[i];
         }
     };
@@ -1096,8 +1112,8 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
                   h2_stream_t s, bool zero_header, bool x_bf16) {
     H2_REQUIRE(n_cols > 0 && d > 0 && d % 4 == 0 && splits_valid(splits) && xpack && ld >= d && ld % 4 == 0,
                H2_ERR_INVALID, "bm_pack: bad argument (d=%d splits=%d)", d, splits);
-    H2_REQUIRE(!x_bf16 || (splits_i8(splits) && n_parts == 1 && !xfull && d % 8 == 0 && ld % 8 == 0), H2_ERR_UNSUPPORTED,
-               "bm_pack: bf16 rows need the int8 digits, a single part and d, ld multiples of 8");
+    H2_REQUIRE(!x_bf16 || (splits_i8(splits) && d % 8 == 0 && ld % 8 == 0 && (!xfull || ld_full % 8 == 0)), H2_ERR_UNSUPPORTED,
+               "bm_pack: bf16 rows need the int8 digits and d, ld multiples of 8");
     H2_REQUIRE(xpack_bytes >= h2_bm_xpack_bytes(n_cols, d, splits) && aligned16(xpack), H2_ERR_WORKSPACE,
                "bm_pack: xpack buffer too small / misaligned");
     H2_REQUIRE(!xfull || (ld_full >= d && ld_full % 4 == 0 && aligned16(xfull)), H2_ERR_ALIGN, "bm_pack: xfull alignment");
@@ -1144,7 +1160,11 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
 }
 
 int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
-                float *xfull, int64_t ld_full, h2_stream_t s) {
+                float *xfull, int64_t ld_full, h2_stream_t s, bool x_bf16) {
+    if (x_bf16) {   // bf16 rows: a pure copy, moved as d / 2 fp32 words (d, ld, ld_full multiples of 8)
+        H2_REQUIRE(d % 8 == 0 && ld % 8 == 0 && ld_full % 8 == 0, H2_ERR_ALIGN, "gather_rows: bf16 rows need d, ld multiples of 8");
+        d /= 2; ld /= 2; ld_full /= 2;
+    }
     H2_REQUIRE(n_cols >= 0 && d > 0 && d % 4 == 0 && xfull && ld % 4 == 0 && ld_full % 4 == 0 && ld >= d && ld_full >= d &&
                aligned16(xfull), H2_ERR_INVALID, "gather_rows: bad argument");
     if (n_cols == 0) return H2_OK;

@@ -298,7 +298,7 @@ int bm_pack_parts(int32_t n_cols, int32_t d, int32_t splits, int32_t n_parts, co
 int bm_spmm_bf16_out(const void *bm_host, const void *bm_dev, int32_t d, int32_t splits, const void *xpack, const float *dinv_row,
                      void *Y, int64_t ldy, int64_t out_col_off, void *partial_ws, size_t partial_bytes, h2_stream_t s);
 int gather_rows(int32_t n_cols, int32_t d, int32_t n_parts, const float *const *ptrs, const int64_t *bounds, int64_t ld,
-                float *xfull, int64_t ld_full, h2_stream_t s);
+                float *xfull, int64_t ld_full, h2_stream_t s, bool x_bf16);
 }
 
 struct RoundParts {   // the round input as row shards (device / peer pointers) + the scratch for its gathered fp32 copy
@@ -315,8 +315,8 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
                             const RoundParts *parts = nullptr, int32_t x_dtype = H2_F32, int32_t y_dtype = H2_F32) {
     cudaStream_t st = (cudaStream_t)s;
     const bool xb = x_dtype == H2_BF16, yb = y_dtype == H2_BF16;   // bf16 rows: ldx / ldy / offsets count bf16 elements
-    H2_REQUIRE(!(xb || yb) || (!parts && !x_offsets && !y_host && d % 8 == 0), H2_ERR_UNSUPPORTED,
-               "h2_graph_round_ex: bf16 rows are supported for plain device rounds with d %% 8 == 0");
+    H2_REQUIRE(!(xb || yb) || (!x_offsets && !y_host && d % 8 == 0), H2_ERR_UNSUPPORTED,
+               "h2_graph_round_ex: bf16 rows are supported for forward device rounds (whole or row-sharded input) with d %% 8 == 0");
     H2_REQUIRE(g && (X || parts) && Y && offsets && d >= 4 && d % 4 == 0, H2_ERR_INVALID, "h2_graph_round: bad argument (d=%d)", d);
     int rc = H2_OK;
     H2_REQUIRE(!g->n_bm || (d <= g->d_max && g->xpack), H2_ERR_WORKSPACE,
@@ -342,12 +342,12 @@ static int graph_round_impl(h2_graph_t *g, int32_t d, const float *X, int64_t ld
         if (g->n_bm && d <= max_w) {
             const int h = g->bm_idx[0];
             rc = bm_pack_parts(g->n_cols, d, g->splits, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, g->dinv[h],
-                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s, false, false);
+                               g->xpack, g->xpack_bytes, g->n_csr || g->n_bm > 1 ? parts->xfull : nullptr, parts->ld_full, s, false, xb);
             if (rc != H2_OK) return rc;
             first_bm = 1;
         } else {
             rc = gather_rows(g->n_cols, d, parts->n_parts, parts->ptrs, parts->bounds, parts->ld, parts->xfull,
-                             parts->ld_full, s);
+                             parts->ld_full, s, xb);
             if (rc != H2_OK) return rc;
         }
         X = parts->xfull;
@@ -419,6 +419,17 @@ extern "C" int h2_graph_round_parts(h2_graph_t *g, int32_t d, int32_t n_parts, c
                                     int64_t ldy, const int64_t *y_offsets_host, h2_stream_t s) {
     RoundParts parts{n_parts, part_ptrs_host, bounds_host, ld_part, x_full, ld_full};
     return graph_round_impl(g, d, nullptr, 0, Y, ldy, y_offsets_host, nullptr, s, nullptr, &parts);
+}
+
+extern "C" int h2_graph_round_parts_ex(h2_graph_t *g, int32_t d, int32_t n_parts, const void *const *part_ptrs_host,
+                                       const int64_t *bounds_host, int64_t ld_part, int32_t x_dtype, void *x_full, int64_t ld_full,
+                                       void *Y, int64_t ldy, int32_t y_dtype, const int64_t *y_offsets_host, h2_stream_t s) {
+    H2_REQUIRE((x_dtype == H2_F32 || x_dtype == H2_BF16) && (y_dtype == H2_F32 || y_dtype == H2_BF16), H2_ERR_INVALID,
+               "h2_graph_round_parts_ex: dtype codes are H2_F32 / H2_BF16");
+    H2_REQUIRE(!g || !g->n_bm || splits_is_i8(g->splits) || (x_dtype == H2_F32 && y_dtype == H2_F32), H2_ERR_UNSUPPORTED,
+               "h2_graph_round_parts_ex: bf16 rows on the tensor-core hops need the int8 digits");
+    RoundParts parts{n_parts, (const float *const *)part_ptrs_host, bounds_host, ld_part, (float *)x_full, ld_full};
+    return graph_round_impl(g, d, nullptr, 0, (float *)Y, ldy, y_offsets_host, nullptr, s, nullptr, &parts, x_dtype, y_dtype);
 }
 
 extern "C" int h2_graph_round(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, float *Y, int64_t ldy,

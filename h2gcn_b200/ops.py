@@ -216,7 +216,7 @@ class HopPlan:
         self.tensor_idx = [k for k in range(H) if fmt[k] == 1]
         self.csr_idx = [k for k in range(H) if fmt[k] == 0]
         self.kernel_name = " + ".join(
-            (["bm_mma_kernel (tcgen05 tile-bitmap, %s) x%d" % (_cabi.SPLITS_NAME[splits], len(self.tensor_idx))] if self.tensor_idx else []) +
+            (["%s (tcgen05 tile-bitmap, %s) x%d" % ("bm_pair_kernel" if splits in (_cabi.H2_SPLITS_I8X2, _cabi.H2_SPLITS_I8X3) else "bm_mma_kernel", _cabi.SPLITS_NAME[splits], len(self.tensor_idx))] if self.tensor_idx else []) +
             (["fused_hops_gather_kernel (CSR gather) over %d hop(s)" % len(self.csr_idx)] if self.csr_idx else []))
 
     def reserve(self, d):
@@ -280,15 +280,25 @@ class HopPlan:
     def run_parts(self, part_ptrs, bounds, ld_part, x_full, out, offsets, d, stream=None):
         """Round whose input is given as row shards (device pointers, possibly PEER memory of other ranks): the
         hop-boundary all-gather happens inside the first kernel of the round (h2_graph_round_parts).  `x_full`
-        [n_cols, d] is scratch for the gathered fp32 copy; the caller brackets the call with cross-rank barriers."""
+        [n_cols, d] is scratch for the gathered copy and has the row type of the shards (fp32 or bf16: ld_part counts
+        elements of that type); `out` may be fp32 or bf16.  The caller brackets the call with cross-rank barriers."""
         require_cuda(x_full, out)
+        dt = {torch.float32: _cabi.H2_F32, torch.bfloat16: _cabi.H2_BF16}
+        if x_full.dtype not in dt or out.dtype not in dt:
+            raise ValueError("fused round: fp32 or bf16 feature matrices")
         P = len(part_ptrs)
         ptrs = (ctypes.c_void_p * P)(*part_ptrs)
         bnd = (ctypes.c_int64 * (P + 1))(*[int(b) for b in bounds])
         yo = (ctypes.c_int64 * len(offsets))(*offsets)
         self.reserve(d)
-        check(lib().h2_graph_round_parts(self._h, d, P, ptrs, bnd, ld_part, ptr(x_full), x_full.stride(0), ptr(out),
-                                         out.stride(0), yo, stream_ptr(stream)))
+        if x_full.dtype == torch.bfloat16 or out.dtype == torch.bfloat16:
+            if d % 8 or ld_part % 8 or x_full.stride(0) % 8 or out.stride(0) % 8 or any(o % 8 for o in offsets):
+                raise ValueError("fused round with bf16 rows: d, leading dimensions and column offsets must be multiples of 8")
+            check(lib().h2_graph_round_parts_ex(self._h, d, P, ptrs, bnd, ld_part, dt[x_full.dtype], ptr(x_full), x_full.stride(0),
+                                                ptr(out), out.stride(0), dt[out.dtype], yo, stream_ptr(stream)))
+        else:
+            check(lib().h2_graph_round_parts(self._h, d, P, ptrs, bnd, ld_part, ptr(x_full), x_full.stride(0), ptr(out),
+                                             out.stride(0), yo, stream_ptr(stream)))
         return out
 
     def close(self):

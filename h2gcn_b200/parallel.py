@@ -165,15 +165,15 @@ class ShardedGraph:
                     raise
                 self._exchange_error = repr(e)
 
-    def input_buffer(self, d):
-        """The rank's input shard [n_local, d] for width d, allocated in symmetric memory (peers map it over NVLink).
-        Writing the round input here makes `round` zero-copy; any other tensor is copied in first."""
-        buf = self._sym.get(d)
+    def input_buffer(self, d, dtype=torch.float32):
+        """The rank's input shard [n_local, d] for width d (fp32 or bf16 rows), allocated in symmetric memory (peers map
+        it over NVLink).  Writing the round input here makes `round` zero-copy; any other tensor is copied in first."""
+        buf = self._sym.get((d, dtype))
         if buf is None:
             rows = int(np.diff(self.bounds).max())
-            t = self._symm_mem.empty((rows, d), dtype=torch.float32, device=self.device)
+            t = self._symm_mem.empty((rows, d), dtype=dtype, device=self.device)
             hdl = self._symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
-            buf = self._sym[d] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
+            buf = self._sym[(d, dtype)] = (t, hdl, [int(p) for p in hdl.buffer_ptrs])
         return buf[0][:self.n_local]
 
     def gathered_input(self, x_local):
@@ -192,14 +192,14 @@ class ShardedGraph:
         if self.world == 1 or self.exchange != "p2p":
             x = self.gathered_input(x_local)
             return self.plan.run(x, y_local, offsets, d=d)
-        mine = self.input_buffer(x_local.shape[1])
+        mine = self.input_buffer(x_local.shape[1], x_local.dtype)
         if mine.data_ptr() != x_local.data_ptr():
             mine.copy_(x_local)
-        t, hdl, ptrs = self._sym[x_local.shape[1]]
-        key = ("full", x_local.shape[1])
+        t, hdl, ptrs = self._sym[(x_local.shape[1], x_local.dtype)]
+        key = ("full", x_local.shape[1], x_local.dtype)
         xf = self._x_full.get(key)
         if xf is None:
-            xf = self._x_full[key] = torch.empty(self.n, x_local.shape[1], dtype=torch.float32, device=self.device)
+            xf = self._x_full[key] = torch.empty(self.n, x_local.shape[1], dtype=x_local.dtype, device=self.device)
         hdl.barrier(channel=0)          # every rank's shard is written
         self.plan.run_parts(ptrs, self.bounds, t.stride(0), xf, y_local, offsets, d)
         hdl.barrier(channel=1)          # every rank has finished reading the shards

@@ -63,5 +63,32 @@ def rmat_graph(scale_n, n_edges, a=0.57, b=0.19, c=0.19, seed=1):
     return _sym_csr(scale_n, src[keep], dst[keep])
 
 
+def chung_lu_graph_device(n, n_edges, gamma=2.5, seed=2, device="cuda"):
+    """Power-law graph (Chung-Lu: both endpoints of every edge draw are sampled with probability ~ w_i,
+    w_i = (i + 64)^(-1/(gamma-1)), so expected degrees follow a power law with exponent gamma; vertex 0 is the largest hub),
+    BASELINE config 5's "synthetic power-law |V|=4M |E|=64M".  Built with torch ON THE DEVICE (64 M draws through a
+    4 M-entry CDF take minutes in numpy and well under a second here), returned as host scipy CSR like the others.
+    Deterministic for a given (n, n_edges, gamma, seed) on the same GPU architecture (Philox)."""
+    import torch
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    w = (torch.arange(n, dtype=torch.float64, device=dev) + 64.0) ** (-1.0 / (gamma - 1.0))
+    cdf = torch.cumsum(w, 0)
+    cdf /= cdf[-1].clone()
+    src = torch.searchsorted(cdf, torch.rand(n_edges, dtype=torch.float64, device=dev, generator=gen), right=True).clamp_(max=n - 1)
+    dst = torch.searchsorted(cdf, torch.rand(n_edges, dtype=torch.float64, device=dev, generator=gen), right=True).clamp_(max=n - 1)
+    keep = src != dst
+    lo, hi = torch.minimum(src[keep], dst[keep]), torch.maximum(src[keep], dst[keep])
+    und = torch.unique(lo * n + hi)                                   # distinct undirected edges
+    lo, hi = und // n, und % n
+    key = torch.sort(torch.cat([lo * n + hi, hi * n + lo]))[0]        # both directions, (row, col) order
+    rows, cols = key // n, (key % n).to(torch.int32)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    indptr_h, cols_h = indptr.cpu().numpy(), cols.cpu().numpy()
+    return sp.csr_matrix((np.ones(len(cols_h), dtype=np.float32), cols_h, indptr_h), shape=(n, n))
+
+
 def features(n, d, seed=0):
     return np.random.default_rng(seed + 1000).standard_normal((n, d)).astype(np.float32)

@@ -255,6 +255,12 @@ int h2_graph_round_multi(h2_graph_t *g, int32_t d, const float *X, int64_t ldx, 
 int h2_graph_round_parts(h2_graph_t *g, int32_t d, int32_t n_parts, const float *const *part_ptrs_host,
                          const int64_t *bounds_host, int64_t ld_part, float *x_full, int64_t ld_full, float *Y, int64_t ldy,
                          const int64_t *y_offsets_host, h2_stream_t s);
+/* the same with bf16 feature rows (BASELINE config 5 on several GPUs): the shards and the gathered copy x_full hold
+ * x_dtype rows (ld_part / ld_full count elements of that type), Y holds y_dtype rows; d, the leading dimensions and the
+ * offsets are multiples of 8 when a bf16 type is involved. */
+int h2_graph_round_parts_ex(h2_graph_t *g, int32_t d, int32_t n_parts, const void *const *part_ptrs_host,
+                            const int64_t *bounds_host, int64_t ld_part, int32_t x_dtype, void *x_full, int64_t ld_full,
+                            void *Y, int64_t ldy, int32_t y_dtype, const int64_t *y_offsets_host, h2_stream_t s);
 /* G[:, 0:d] (+)= sum_s T[:, s*d : (s+1)*d], optionally masked by (mask_src > 0) (ReLU gradient).  accumulate != 0: add to G. */
 int h2_sum_slices_f32(int32_t n_rows, int32_t d, int32_t n_slices, const float *T, int64_t ldt, float *G, int64_t ldg,
                       int32_t accumulate, const float *mask_src, int64_t ld_mask, h2_stream_t s);

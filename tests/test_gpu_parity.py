@@ -878,3 +878,31 @@ def test_bf16_feature_rows(dev, mode, d):
     y32 = torch.empty(n, 2 * d, device=dev)
     HopPlan(hops, mode=mode).run(x, y32, [0, d])
     assert util.rel_err(y32.cpu().numpy(), ref) <= 1e-5
+
+
+# ---- g2 on several GPUs: row shards of bf16 (and fp32) rows, gathered inside the first kernel of the round -------------
+@pytest.mark.parametrize("mode", ["csr", "tensor", "auto"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_row_sharded_input_on_one_gpu(dev, mode, dtype):
+    """h2_graph_round_parts / _parts_ex with three row shards that all live on THIS GPU (the entry points take any device
+    pointers; on a multi-GPU box the peers' shards are symmetric-memory pointers, tests/test_multi_gpu.py): the result is
+    BIT-identical to the round on the whole matrix, the gathered copy equals the input, in both row types."""
+    from h2gcn_b200.ops import HopPlan
+    z = util.load_golden("planetoid_cora")
+    n, d = int(z["feat_shape"][0]), 72
+    hops = _norm_hops(dev, z)
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    x = torch.from_numpy(np.random.default_rng(5).standard_normal((n, d)).astype(np.float32)).to(dev).to(td)
+    bounds = [0, 1000, 1000 + 64 * 13 + 5, n]                      # uneven, not chunk-aligned
+    parts = [x[bounds[q]:bounds[q + 1]].clone() for q in range(3)]  # separate allocations
+    assert all(p.data_ptr() % 16 == 0 for p in parts)
+    plan = HopPlan(hops, mode=mode)
+    y_ref = torch.empty(n, 2 * d, device=dev, dtype=td)
+    plan.run(x, y_ref, [0, d])
+    y = torch.full((n, 2 * d), float("nan"), device=dev, dtype=td)
+    x_full = torch.full((n, d), float("nan"), device=dev, dtype=td)
+    plan.run_parts([p.data_ptr() for p in parts], bounds, d, x_full, y, [0, d], d)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    if plan.csr_idx or mode == "csr":
+        assert torch.equal(x_full, x), "the gathered copy the CSR hops read"

@@ -51,6 +51,15 @@ def _worker(rank, world, port, graph_kind, ret):
         ref = full[g.row_begin:g.row_end]
         err = float(np.abs(outs["p2p"] - ref).max() / np.abs(full).max())
         assert err <= 1e-4, err
+        # bf16 rows (BASELINE config 5): shards, gathered copy and output in bf16; within one bf16 rounding of the exact result
+        xb = torch.from_numpy(x).to(dev).to(torch.bfloat16)
+        yb = torch.full((g.n_local, 2 * d), float("nan"), device=dev, dtype=torch.bfloat16)
+        g.round(xb[g.row_begin:g.row_end].contiguous(), yb, [0, d])
+        torch.cuda.synchronize()
+        x64 = xb.float().cpu().numpy().astype(np.float64)
+        refb = np.concatenate([a1[g.row_begin:g.row_end].astype(np.float64) @ x64, a2[g.row_begin:g.row_end].astype(np.float64) @ x64], axis=1)
+        errb = np.abs(yb.float().cpu().numpy() - refb)
+        assert (errb <= 2.0 ** -8 * np.abs(refb) + 1e-6 * np.abs(refb).max()).all()
         ret[rank] = (g.row_begin, g.row_end, err, g.plan.kernel_name)
     finally:
         dist.destroy_process_group()
