@@ -824,6 +824,9 @@ def main_cfg5(args):
                      explicit_vals=False, balance="auto")
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0
+    sys.stderr.write(f"[cfg5] rank {rank}: rows [{g.row_begin}, {g.row_end}) nnz1+nnz2 {g.nnz_local} max row {g.max_row_nnz} "
+                     f"partition {g.balance} exchange {g.exchange} kernel {g.plan.kernel_name} precompute {t_pre:.2f} s\n")
+    sys.stderr.flush()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1005)
     x_all = torch.randn(n, d, device=dev, generator=gen).to(torch.bfloat16)          # the same matrix on every rank

@@ -857,12 +857,16 @@ struct BmPairFix { int32_t tile, group, slot_begin, n_slots; };
 struct BmPairParams {
     const int32_t *unit_chunk; const unsigned long long *bits; const BmPairSeg *seg; const int32_t *cta_seg_ptr;
     const uint8_t *xpack; const float *xstep; const float *dinv_row; float *Y; float *partial; const BmPairFix *fix;
-    uint32_t *sync; int32_t *status; int32_t n_fix; int64_t ldy; int32_t n_rows, d, n_groups_fh, y_bf16;
+    uint32_t *sync; int32_t *status; int32_t n_fix; int64_t ldy; int32_t n_rows, d, n_groups_fh, y_bf16, safe_handover;
 };
 void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int n_pairs_max, std::vector<BmPairSeg> &segs,
                    std::vector<int32_t> &pair_ptr, std::vector<BmPairFix> &fixes, int *n_slots_out);
 int pair_launch(int S, int fh, int n_pairs, const BmPairParams &p, cudaStream_t st);
+#ifdef H2_BM_PAIR_SEG_UNITS
+constexpr int kPairMaxSegUnitsHost = H2_BM_PAIR_SEG_UNITS;
+#else
 constexpr int kPairMaxSegUnitsHost = 2048;
+#endif
 static size_t pair_sched_bytes(int64_t nt, int64_t n_units, int ng) {
     const size_t max_segs = (size_t)(kNumSms / 2 + ng * (nt + 1) + ng * (n_units / kPairMaxSegUnitsHost + 1) + 2);
     return align_up_sz(max_segs * sizeof(BmPairSeg), 256) + align_up_sz((size_t)(kNumSms / 2 + 2) * 4, 256) +
@@ -1292,6 +1296,14 @@ static int bm_spmm_impl(const void *bm_host, const void *bm_dev, int32_t d, int3
         pp.status = (int32_t *)(const_cast<char *>(base) + h->off_status);
         pp.ldy = ldy;
         pp.n_rows = h->n_rows; pp.d = d; pp.n_groups_fh = std::max(2, groups_for(d, fh));
+        {
+            // operands of one launch: packed X' tiles + bitmaps.  Beyond ~half of the 126 MB L2 they stream from DRAM, the
+            // tensor pipe starves and the cross-CTA hand-over needs its cluster-scope release (bm_pair.cu, produce()).
+            // H2_BM_PAIR_SAFE = 0 / 1 forces the choice (measurements, tests).
+            static const int forced = [] { const char *e = getenv("H2_BM_PAIR_SAFE"); return e ? atoi(e) : -1; }();
+            const double operand_bytes = (double)h2_bm_xpack_bytes(h->n_cols, d, splits) + (double)h->n_units * kTileRows * 8;
+            pp.safe_handover = forced >= 0 ? forced : (operand_bytes > 48.0 * 1024 * 1024 ? 1 : 0);
+        }
         return pair_launch(splits_pieces(splits), fh, sp.n_ctas, pp, st);
     }
     H2_REQUIRE(!y_bf16, H2_ERR_UNSUPPORTED, "h2_bm_spmm: bf16 rows are implemented for the int8 digits only");

@@ -204,8 +204,37 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Hand-overs BETWEEN the two CTAs of a pair (producer / epilogue warps of either CTA -> the leader's MMA thread).
+// Formally they need release / acquire at CLUSTER scope: with the default (.cta) scope nothing orders the peer CTA's
+// TMA-landed B half and tcgen05.st A rows before the MMA the leader issues on its behalf.  Measured (r02, profiles/README.md):
+// with plain arrives a round is always right while the operands sit in L2 (the MMA thread trails the arrivals by hundreds of
+// cycles), but on wide row shards whose operands stream from DRAM the MMA is issued the moment the last arrival lands, and
+// ~1 launch in 3 had ONE stale 128-row half of one tile (n_cols = 262144; a 1 us sleep before the arrive hides it, a
+// tcgen05.ld read-back of the staged rows does not, acquire.cluster on the waiting side alone does not; release.cluster on
+// the arriving side fixes it: 0 of 60 launches wrong).  The release costs a ~2.5 k-cycle fence:
+//   * accumulator hand-over (once per segment and warp): always release.cluster (mbar_arrive_remote);
+//   * operand hand-over (once per unit): fence_release_cluster() + relaxed arrives in batches, only when the launch is
+//     flagged safe_handover (operands larger than L2: the starved tensor pipe hides the fence) — bm_pair.cu, produce().
+// H2_BM_PAIR_SCOPE_MODE (measurement knob): 0 = .cta on both sides (the old behaviour), 1 = release.cluster arrive only,
+// 2 = acquire.cluster wait only, 3 = both.
+#ifndef H2_BM_PAIR_SCOPE_MODE
+#define H2_BM_PAIR_SCOPE_MODE 3
+#endif
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+#if H2_BM_PAIR_SCOPE_MODE == 0 || H2_BM_PAIR_SCOPE_MODE == 2
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
+// the two halves of a release.cluster arrive, for callers that publish several barriers behind one fence
+__device__ __forceinline__ void fence_release_cluster() {
+#if H2_BM_PAIR_SCOPE_MODE == 1 || H2_BM_PAIR_SCOPE_MODE == 3
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals come from the peer CTA too
     uint32_t done;
@@ -213,7 +242,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
+#if H2_BM_PAIR_SCOPE_MODE == 0 || H2_BM_PAIR_SCOPE_MODE == 1
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);

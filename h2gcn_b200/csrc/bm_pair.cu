@@ -38,7 +38,11 @@ constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;    // 320
 // register cap: 320 x 144 + 256 x 64 (one CSR-gather CTA of the same round) <= 64 K registers per SM, so that the hop-1
 // gather can share the SM with the persistent MMA CTA
 constexpr int kPairMaxRegs = 144;
+#ifdef H2_BM_PAIR_SEG_UNITS
+constexpr int kPairMaxSegUnits = H2_BM_PAIR_SEG_UNITS;      // test builds: force many accumulator cuts on small graphs
+#else
 constexpr int kPairMaxSegUnits = 2048;                      // int32 accumulators: 2^17 columns of at most 64 * 128
+#endif
 
 struct BmPairSeg {        // one contiguous run of units inside one (row tile, column group), handled by one CTA pair
     int32_t tile, unit_begin, unit_end, group;
@@ -92,6 +96,7 @@ struct BmPairParams {
     int64_t ldy;
     int32_t n_rows, d, n_groups_fh;
     int32_t y_bf16;              // Y rows hold bf16 (ldy counts bf16 elements): one rounding at the store
+    int32_t safe_handover;       // 1: cluster-scope release fence before the producers' arrives (operands streaming from DRAM)
 };
 
 // 4 consecutive output features at element offset `off` of the Y buffer (fp32 rows or bf16 rows)
@@ -149,6 +154,9 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     constexpr int kAhead = (kAStg < kBStg ? kAStg : kBStg) - 2;
 #endif
     static_assert(kAhead >= 0 && kAhead < kAStg && kAhead < kBStg, "run-ahead must stay inside both rings");
+    constexpr int kSafeBatch = 4;    // units per release fence with p.safe_handover (1 without: lowest hand-over latency)
+    // a batch holds A stages of units u, u + G, ..., u + G (batch - 1): each must have been freed by a unit OLDER than u
+    static_assert(kPairGroups * (kSafeBatch - 1) < kAStg && kPairGroups * (kSafeBatch - 1) < kBStg, "arrive batch must stay inside the A / B rings");
     // D int32 | A, B signed int8 | N | M = 256 (128 rows per CTA)
     constexpr uint32_t kN1 = Cfg::kTwoInstr ? 256 : N, kN2 = N - kN1;
     constexpr uint32_t kIdesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((kN1 >> 3) << 17) | ((256u >> 4) << 24);
@@ -293,6 +301,9 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
         PT_DECL();
         // this group's units hnd in [from, to) of a segment whose first unit is the it0-th unit of this CTA pair
         auto produce = [&](uint32_t it0, int from, int to) {
+            uint32_t pend_first = 0;   // A stage of the batch's first unit; the others follow every kPairGroups stages
+            int n_pend = 0;
+            const int arrive_batch = p.safe_handover ? kSafeBatch : 1;
             const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it0 % kPairGroups)) % kPairGroups);
             const int first = from + (int)((uint32_t)(skip + kPairGroups - from % kPairGroups) % kPairGroups);
             for (int hnd = first; hnd < to; hnd += kPairGroups) {
@@ -328,10 +339,28 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
 #endif
                 tc_fence_after();
                 cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * 16, a);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // ~22 cycles (tools/umma_i8_probe.cu part 3)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(full_a_leader + 8 * sa);
+                // Hand-over to the leader's MMA thread.  p.safe_handover: ONE cluster-scope release fence per batch of
+                // kSafeBatch units of this group, then a plain arrive per staged unit — what the memory model asks for when a
+                // thread of the PEER CTA publishes operands (its TMA-landed B half, its tcgen05.st A rows) to the MMA thread of
+                // the leader.  The fence costs ~2.5 k cycles: per unit it made the producers the bottleneck (38 -> 59 us per
+                // tensor hop at the north-star point, 52 us in batches of 4), so rounds whose operands sit in L2 keep the
+                // plain arrive (see the header: there the tensor pipe trails the arrivals by hundreds of cycles and the
+                // hazard has never been observed; r02 stress tests), and shards whose operands stream from DRAM — where the
+                // MMA is issued the moment the last arrival lands, and 1 launch in 3 had one stale 128-row half — take the fence,
+                // which the starved tensor pipe hides.  Stages of a batch: units u, u + 2, ... < u + kAStg.
+                if (n_pend++ == 0) pend_first = sa;
+                if (n_pend == arrive_batch || hnd + kPairGroups >= to) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // ~22 cycles (tools/umma_i8_probe.cu part 3)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.safe_handover) fence_release_cluster();
+#pragma unroll
+                        for (int q = 0; q < kSafeBatch; ++q)
+                            if (q < n_pend) mbar_arrive_remote_relaxed(full_a_leader + 8 * ((pend_first + q * kPairGroups) % kAStg));
+                    }
+                    n_pend = 0;
+                }
 #ifdef H2_BM_TRACE
                 pt_acc__[2] += clock64() - pt_x1;
                 if (quarter == 0 && lane == 0) PT_UNIT(4, iu);

@@ -906,3 +906,52 @@ def test_row_sharded_input_on_one_gpu(dev, mode, dtype):
     assert torch.equal(y, y_ref)
     if plan.csr_idx or mode == "csr":
         assert torch.equal(x_full, x), "the gathered copy the CSR hops read"
+
+
+# ---- r02: cross-CTA hand-over of the pair kernel on shards whose operands stream from DRAM ----------------------------
+def test_pair_kernel_wide_shard_is_repeatable(dev):
+    """A row shard with 2^18 columns and d = 256: ~200 MB of packed operands per launch, far beyond L2, so the tensor pipe
+    is starved and the MMA of a unit is issued the moment its last operand arrival lands.  Before the cluster-scope
+    release on the producers' arrives (bm_common.cuh) about one launch in three had ONE stale 128-row half of one tile
+    here (and on BASELINE config 4 / 5 shards).  Every launch must agree with the fp32 CSR gather."""
+    from h2gcn_b200 import ops
+    from h2gcn_b200.parallel import ShardedGraph
+    from h2gcn_b200.utils import synth
+    n, rows, d = 262144, 4096, 256
+    adj = synth.chung_lu_graph_device(n, 16 * n, gamma=2.5, seed=2, device=dev)
+    g = ShardedGraph(adj, 0, 1, dev, factored=True, explicit_vals=False, mode="csr")
+    h = g.hops[1]
+    e = int(h.rowptr[rows].item())
+    shard = [ops.SparseTensor(h.rowptr[:rows + 1].contiguous(), h.col[:e].contiguous(), None, (rows, n), row_begin=0, dinv=h.dinv)]
+    x = torch.randn(n, d, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    y0 = torch.empty(rows, d, device=dev)
+    ops.HopPlan(shard, factored=True, mode="csr").run(x, y0, [0])
+    pt = ops.HopPlan(shard, factored=True, mode="tensor")
+    scale = float(y0.abs().max())
+    first = None
+    for rep in range(12):
+        y1 = torch.full((rows, d), float("nan"), device=dev)
+        pt.run(x, y1, [0])
+        torch.cuda.synchronize()
+        err = float(torch.nan_to_num((y1 - y0).abs(), nan=float("inf")).max()) / scale
+        assert err <= 1e-4, f"launch {rep}: {err:.3e}"
+        first = y1 if first is None else first
+        assert torch.equal(first, y1), f"launch {rep} differs from launch 0"
+
+
+def test_pair_kernel_north_star_is_repeatable(dev):
+    """The L2-resident regime keeps the plain (CTA-scope) operand hand-over: 150 launches, bit-identical outputs."""
+    from h2gcn_b200 import ops
+    from h2gcn_b200.parallel import ShardedGraph
+    from h2gcn_b200.utils import synth
+    n, d = 10000, 128
+    g = ShardedGraph(synth.uniform_graph(n, 200000, seed=0), 0, 1, dev)
+    x = torch.from_numpy(synth.features(n, d, 0)).to(dev)
+    y0 = torch.empty(n, 2 * d, device=dev)
+    g.round(x, y0, [0, d])
+    torch.cuda.synchronize()
+    for rep in range(150):
+        y = torch.full((n, 2 * d), float("nan"), device=dev)
+        g.round(x, y, [0, d])
+        torch.cuda.synchronize()
+        assert torch.equal(y, y0), f"launch {rep}"
