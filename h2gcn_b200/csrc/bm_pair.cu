@@ -141,7 +141,9 @@ __device__ __forceinline__ void red_release_gpu_add(int32_t *p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int S, int FH>
+// SAFE: the producers' operand hand-over carries a cluster-scope release fence (p.safe_handover launches); the plain
+// instantiation keeps the per-unit arrive of the L2-resident regime free of the batching bookkeeping
+template <int S, int FH, bool SAFE>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kernel(const __grid_constant__ BmPairParams p) {
     using Cfg = PairCfg<S, FH>;
     constexpr int NBH = Cfg::NBH, N = Cfg::N;
@@ -154,7 +156,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     constexpr int kAhead = (kAStg < kBStg ? kAStg : kBStg) - 2;
 #endif
     static_assert(kAhead >= 0 && kAhead < kAStg && kAhead < kBStg, "run-ahead must stay inside both rings");
-    constexpr int kSafeBatch = 4;    // units per release fence with p.safe_handover (1 without: lowest hand-over latency)
+    constexpr int kSafeBatch = SAFE ? 4 : 1;   // units per release fence (1 without the fence: lowest hand-over latency)
     // a batch holds A stages of units u, u + G, ..., u + G (batch - 1): each must have been freed by a unit OLDER than u
     static_assert(kPairGroups * (kSafeBatch - 1) < kAStg && kPairGroups * (kSafeBatch - 1) < kBStg, "arrive batch must stay inside the A / B rings");
     // D int32 | A, B signed int8 | N | M = 256 (128 rows per CTA)
@@ -303,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
         auto produce = [&](uint32_t it0, int from, int to) {
             uint32_t pend_first = 0;   // A stage of the batch's first unit; the others follow every kPairGroups stages
             int n_pend = 0;
-            const int arrive_batch = p.safe_handover ? kSafeBatch : 1;
+            constexpr int arrive_batch = kSafeBatch;
             const int skip = (int)((uint32_t)(grp + kPairGroups - (int)(it0 % kPairGroups)) % kPairGroups);
             const int first = from + (int)((uint32_t)(skip + kPairGroups - from % kPairGroups) % kPairGroups);
             for (int hnd = first; hnd < to; hnd += kPairGroups) {
@@ -354,10 +356,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.safe_handover) fence_release_cluster();
+                        if constexpr (SAFE) {
+                            fence_release_cluster();
 #pragma unroll
-                        for (int q = 0; q < kSafeBatch; ++q)
-                            if (q < n_pend) mbar_arrive_remote_relaxed(full_a_leader + 8 * ((pend_first + q * kPairGroups) % kAStg));
+                            for (int q = 0; q < kSafeBatch; ++q)
+                                if (q < n_pend) mbar_arrive_remote_relaxed(full_a_leader + 8 * ((pend_first + q * kPairGroups) % kAStg));
+                        } else {
+                            mbar_arrive_remote_cta(full_a_leader + 8 * sa);
+                        }
                     }
                     n_pend = 0;
                 }
@@ -759,10 +765,10 @@ void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int 
 
 size_t pair_partial_bytes(int n_slots, int fh) { return (size_t)n_slots * kTileRows * (2 * fh) * 4; }
 
-template <int S, int FH>
-static int pair_launch_t(int n_pairs, const BmPairParams &p, cudaStream_t st) {
+template <int S, int FH, bool SAFE>
+static int pair_launch_ts(int n_pairs, const BmPairParams &p, cudaStream_t st) {
     using Cfg = PairCfg<S, FH>;
-    auto kern = bm_pair_kernel<S, FH>;
+    auto kern = bm_pair_kernel<S, FH, SAFE>;
     static bool attr_done[64] = {};
     int dev = 0;
     H2_CUDA(cudaGetDevice(&dev));
@@ -773,6 +779,11 @@ static int pair_launch_t(int n_pairs, const BmPairParams &p, cudaStream_t st) {
     kern<<<2 * n_pairs, kPairThreads, Cfg::kSmem, st>>>(p);   // __cluster_dims__(2, 1, 1)
     H2_LAUNCHED("bm_pair_kernel");
     return H2_OK;
+}
+
+template <int S, int FH>
+static int pair_launch_t(int n_pairs, const BmPairParams &p, cudaStream_t st) {
+    return p.safe_handover ? pair_launch_ts<S, FH, true>(n_pairs, p, st) : pair_launch_ts<S, FH, false>(n_pairs, p, st);
 }
 
 int pair_launch(int S, int fh, int n_pairs, const BmPairParams &p, cudaStream_t st) {
