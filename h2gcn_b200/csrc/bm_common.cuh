@@ -233,6 +233,9 @@ __device__ __forceinline__ void fence_release_cluster() {
     asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {   // a barrier of THIS CTA: release at CTA scope
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {   // default semantics: release at CTA scope
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

@@ -171,7 +171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     const uint32_t bits_base = smem_base + kBStg * kBStride;
     const unsigned long long *bits_gen = reinterpret_cast<const unsigned long long *>(smem_raw + (bits_base - smem_raw_u32));
     float *stage_gen = reinterpret_cast<float *>(smem_raw + (bits_base - smem_raw_u32) + kBStg * kBitsBytes);
-    __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStg + 2];
+    __shared__ uint64_t s_bar[2 * kAStg + 2 * kBStg + 3];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_chunk[32];
     __shared__ bool s_last;
@@ -183,7 +183,8 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     const uint32_t bar_full_b = bar0 + 8 * (2 * kAStg);                // local TMA
     const uint32_t bar_empty_b = bar0 + 8 * (2 * kAStg + kBStg);       // multicast commit
     const uint32_t bar_acc_full = bar0 + 8 * (2 * kAStg + 2 * kBStg);  // multicast commit
-    const uint32_t bar_acc_empty = bar_acc_full + 8;                   // leader only: both CTAs' epilogue warps
+    const uint32_t bar_acc_empty = bar_acc_full + 8;                   // leader only: its 8 epilogue warps + the peer's relay
+    const uint32_t bar_acc_drained = bar_acc_full + 16;                // peer only: its 8 epilogue warps (local)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -209,7 +210,8 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
             mbar_init(bar_empty_b + 8 * s, 1);
         }
         mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 2 * 4 * kPairGroups);
+        mbar_init(bar_acc_empty, 4 * kPairGroups + 1);
+        mbar_init(bar_acc_drained, 4 * kPairGroups);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // the same warp of both CTAs
@@ -289,6 +291,17 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
 #ifdef H2_BM_TRACE
             g_pair_trace[blockIdx.x * 16 + 10] = it; g_pair_trace[blockIdx.x * 16 + 11] = n_work;
 #endif
+        } else if (rank != 0 && elect_one()) {
+            // ===== peer CTA: relay of the accumulator hand-over =====
+            // The peer's epilogue warps arrive on a LOCAL barrier (CTA scope is all they need); this otherwise idle thread
+            // forwards every completed phase to the leader's barrier with the cluster-scope release the hand-over between
+            // CTAs asks for (bm_common.cuh).  The ~2.5 k-cycle fence of that release used to sit in every epilogue warp
+            // between its accumulator drain and its write-out, i.e. on the critical path at the end of every pair.
+            const uint32_t acc_empty_leader = mapa_u32(bar_acc_empty, 0);
+            for (int w = 0; w < n_work; ++w) {
+                mbar_wait(bar_acc_drained, w & 1);
+                mbar_arrive_remote(acc_empty_leader);
+            }
         }
         __syncwarp();
     } else {
@@ -296,7 +309,8 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
         const int grp = warp >> 2, quarter = warp & 3;
         const int r = quarter * 32 + lane;                       // row inside this CTA's 128-row half
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t full_a_leader = mapa_u32(bar_full_a, 0), acc_empty_leader = mapa_u32(bar_acc_empty, 0);
+        const uint32_t full_a_leader = mapa_u32(bar_full_a, 0);
+        const uint32_t acc_done_local = rank == 0 ? bar_acc_empty : bar_acc_drained;   // see the relay in the peer's warp 9
         float *stage = stage_gen + warp * (32 * kStageStride);
         const float xstep = __ldg(p.xstep);
         uint32_t it = 0, acc_it = 0;   // units / accumulator phases before this segment
@@ -441,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
                     if (hb == 1 && c0 + 32 >= FH) {   // last columns read: this warp is done with the accumulators
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+                        if (lane == 0) mbar_arrive_local(acc_done_local);
                     }
 #pragma unroll
                     for (int q = 0; q < 16; q += 4) {
