@@ -159,6 +159,28 @@ def sample_hops_cpu(adj, rows, deg2_all):
     return out
 
 
+def full_shard_check(g, x_all, y, d):
+    """EVERY row of the rank's tensor-core hops against the same hops on the fp32 CSR gather kernel (an independent code
+    path over the same device arrays), outside the timed region: the row sample above would miss an error confined to one
+    128-row half of one tile (cross-CTA hand-over)."""
+    import torch
+    from h2gcn_b200 import ops
+    out = {}
+    for h in g.plan.tensor_idx:
+        ref = torch.empty(g.n_local, d, device=y.device, dtype=y.dtype)
+        ops.HopPlan([g.hops[h]], factored=True, mode="csr").run(x_all, ref, [0])
+        got = y[:, h * d:(h + 1) * d].float()
+        ref = ref.float()
+        scale = float(ref.abs().max())
+        err = (got - ref).abs()
+        rn = ref.abs().amax(dim=1)
+        live = rn > 0
+        out[f"hop{h + 1}"] = {"rows": int(g.n_local), "max_abs_err_over_max_abs_ref": float(err.max()) / max(scale, 1e-30),
+                             "row_wise_max_rel_err": float((err.amax(dim=1)[live] / rn[live]).max()) if bool(live.any()) else 0.0}
+        del ref, got, err
+    return out
+
+
 def pick_sample_rows(adj, budget_nnz, seed=7):
     """Seeded row sample whose 2-hop rows hold about `budget_nnz` entries (estimated from sum of neighbour degrees)."""
     rng = np.random.default_rng(seed)
@@ -748,6 +770,8 @@ def main_multi(args):
         parity.update({"against": "oracle C port on the host: 2-hop rows rebuilt from the definition with scipy, in-order fp32 sums",
                        "rows_checked": int(len(rows)), "entries_checked": int(len(c1) + len(c2)),
                        "deg2_of_sample_matches_gpu": bool(np.array_equal(deg2_cpu, deg_all[rows]))})
+    if rank == 0 and parity is not None and g.plan.tensor_idx:
+        parity["full_shard_tensor_vs_csr"] = full_shard_check(g, torch.from_numpy(x_full).to(dev), y, d)
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -915,6 +939,9 @@ def main_cfg5(args):
                        "against": "oracle C port on the host (in-order fp32 sums) on the bf16-rounded inputs; 2-hop rows rebuilt from the definition with scipy",
                        "rows_checked": int(len(rows)), "entries_checked": int(len(c1) + len(c2)),
                        "deg2_of_sample_matches_gpu": bool(np.array_equal(np.diff(rp2), deg_all[rows]))})
+    if rank == 0 and parity is not None and g.plan.tensor_idx:
+        parity["full_shard_tensor_vs_csr"] = full_shard_check(g, torch.from_numpy(x_host).to(dev).to(torch.bfloat16), y, d)
+        parity["full_shard_note"] = "both sides round to bf16 once: up to one bf16 ulp (2^-7 relative) apart"
     if rank != 0:
         dist.destroy_process_group()
         return
