@@ -27,6 +27,7 @@
 // rotate+mask words -> `tcgen05.st` -> wait::st -> remote arrive on the leader's barrier), then epilogue; warp 8 = TMA
 // (`cp.async.bulk`: B half + expansion constants + 1 KB of bitmap per unit); warp 9 = TMEM allocation and, in the
 // leader CTA, the ONE thread that issues every MMA / commit for both CTAs.
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "bm_common.cuh"
@@ -776,6 +777,72 @@ void pair_schedule(const std::vector<int64_t> &tp, int64_t n_units, int ng, int 
         }
     *n_slots_out = n_slots;
 }
+
+}  // namespace h2
+
+// Host-only self-check of the pair schedule (no GPU needed: the CPU test suite calls it through ctypes).  `tile_units[t]` =
+// non-empty units of row tile t.  Builds the schedule for `ng` column groups on `n_pairs` CTA pairs and verifies its
+// invariants; returns 0 and fills stats[0..7] = {segments, split items, slots, longest segment, max units of a pair,
+// min units of a pair, designated finishers, pairs used}, or a negative code naming the violated invariant.
+extern "C" int h2_debug_pair_schedule_check(int32_t n_tiles, const int64_t *tile_units, int32_t ng, int32_t n_pairs, int64_t *stats) {
+    using namespace h2;
+    if (n_tiles < 0 || !tile_units || ng < 1 || n_pairs < 1 || !stats) return -100;
+    std::vector<int64_t> tp((size_t)n_tiles + 1, 0);
+    for (int t = 0; t < n_tiles; ++t) { if (tile_units[t] < 0) return -100; tp[t + 1] = tp[t] + tile_units[t]; }
+    const int64_t n_units = tp[n_tiles];
+    std::vector<BmPairSeg> segs;
+    std::vector<int32_t> ptr;
+    std::vector<BmPairFix> fixes;
+    int n_slots = 0;
+    pair_schedule(tp, n_units, ng, n_pairs, segs, ptr, fixes, &n_slots);
+    if (n_units * ng == 0) return segs.empty() ? 0 : -1;
+    const int G = (int)ptr.size() - 1;
+    if (G < 1 || G > n_pairs || ptr[0] != 0 || ptr[G] != (int)segs.size()) return -2;
+    // every (group, unit) exactly once, in group-major unit order across the pairs
+    int64_t q = 0, longest = 0, max_pair = 0, min_pair = INT64_MAX, finishers = 0, used = 0;
+    for (int c = 0; c < G; ++c) {
+        if (ptr[c + 1] < ptr[c]) return -3;
+        int64_t units = 0;
+        for (int i = ptr[c]; i < ptr[c + 1]; ++i) {
+            const BmPairSeg &sg = segs[i];
+            const int64_t len = (int64_t)sg.unit_end - sg.unit_begin;
+            if (len <= 0 || len > kPairMaxSegUnits) return -4;                                  // int32 accumulators
+            if (sg.tile < 0 || sg.tile >= n_tiles || sg.group < 0 || sg.group >= ng) return -5;
+            if (sg.unit_begin < tp[sg.tile] || sg.unit_end > tp[sg.tile + 1]) return -6;       // inside ONE row tile
+            if ((int64_t)sg.group * n_units + sg.unit_begin != q) return -7;                    // contiguous, nothing twice
+            q += len;
+            units += len;
+            longest = std::max(longest, len);
+            const int ns = sg.n_slots < 0 ? -sg.n_slots : sg.n_slots;
+            const bool whole = sg.unit_begin == tp[sg.tile] && sg.unit_end == tp[sg.tile + 1];
+            if (whole != (ns == 0)) return -8;                                                  // split items have slots
+            if (ns && (ns < 2 || sg.slot < sg.slot_begin || sg.slot >= sg.slot_begin + ns || sg.slot_begin < 0 ||
+                       sg.slot_begin + ns > n_slots || sg.fix < 0 || sg.fix >= (int)fixes.size())) return -9;
+            if (sg.n_slots < 0) { ++finishers; if (i != ptr[c + 1] - 1) return -10; }           // a finisher ends its pair
+        }
+        if (units) { ++used; max_pair = std::max(max_pair, units); min_pair = std::min(min_pair, units); }
+    }
+    if (q != n_units * ng) return -11;
+    // per split item: consecutive slots in unit order, one counter, at most one finisher
+    for (size_t f = 0; f < fixes.size(); ++f) {
+        int seen = 0, fin = 0;
+        int64_t next_unit = -1;
+        for (const BmPairSeg &sg : segs) {
+            if (sg.n_slots == 0 || sg.fix != (int)f) continue;
+            if (sg.tile != fixes[f].tile || sg.group != fixes[f].group || sg.slot != fixes[f].slot_begin + seen) return -12;
+            if (next_unit >= 0 && sg.unit_begin != next_unit) return -13;
+            next_unit = sg.unit_end;
+            ++seen;
+            fin += sg.n_slots < 0;
+        }
+        if (seen != fixes[f].n_slots || fin > 1) return -14;
+    }
+    stats[0] = (int64_t)segs.size(); stats[1] = (int64_t)fixes.size(); stats[2] = n_slots; stats[3] = longest;
+    stats[4] = max_pair; stats[5] = used ? min_pair : 0; stats[6] = finishers; stats[7] = used;
+    return 0;
+}
+
+namespace h2 {
 
 size_t pair_partial_bytes(int n_slots, int fh) { return (size_t)n_slots * kTileRows * (2 * fh) * 4; }
 
