@@ -157,7 +157,10 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kern
     constexpr int kAhead = (kAStg < kBStg ? kAStg : kBStg) - 2;
 #endif
     static_assert(kAhead >= 0 && kAhead < kAStg && kAhead < kBStg, "run-ahead must stay inside both rings");
-    constexpr int kSafeBatch = SAFE ? 4 : 1;   // units per release fence (1 without the fence: lowest hand-over latency)
+#ifndef H2_BM_PAIR_SAFE_BATCH
+#define H2_BM_PAIR_SAFE_BATCH 4
+#endif
+    constexpr int kSafeBatch = SAFE ? H2_BM_PAIR_SAFE_BATCH : 1;   // units per release fence (1 without the fence: lowest hand-over latency)
     // a batch holds A stages of units u, u + G, ..., u + G (batch - 1): each must have been freed by a unit OLDER than u
     static_assert(kPairGroups * (kSafeBatch - 1) < kAStg && kPairGroups * (kSafeBatch - 1) < kBStg, "arrive batch must stay inside the A / B rings");
     // D int32 | A, B signed int8 | N | M = 256 (128 rows per CTA)
