@@ -2,7 +2,7 @@
 slots: 0 start, 1 end, per segment w: 2+6w mma-thread reaches segment, 3+6w acc_empty seen, 4+6w last issue done,
 5+6w producer reaches epilogue wait, 6+6w acc_full seen, 7+6w epilogue done."""
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from h2gcn_b200.parallel import ShardedGraph
 from h2gcn_b200.utils import synth
 from h2gcn_b200 import _cabi

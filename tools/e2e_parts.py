@@ -1,6 +1,6 @@
 """Where the end-to-end (host-buffer) time goes: raw PCIe copies vs the h2_graph_round_host call."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 dev = torch.device('cuda:0')
 n, d = 10000, 128
 xh = torch.randn(n, d).pin_memory(); yh = torch.empty(n, 2 * d).pin_memory()

@@ -1,6 +1,6 @@
 """Back-to-back (pipelined, 2 caller streams, rotating replicas) rate of: the full round, the tensor hop alone, the CSR hop alone."""
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from h2gcn_b200.parallel import ShardedGraph
 from h2gcn_b200.ops import HopPlan
 from h2gcn_b200.utils import synth

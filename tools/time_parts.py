@@ -1,6 +1,6 @@
 """Times the parts of one fused round separately (CUDA events, L2 flushed before every launch sequence)."""
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from h2gcn_b200.parallel import ShardedGraph
 from h2gcn_b200.ops import HopPlan
 from h2gcn_b200.utils import synth
