@@ -207,11 +207,8 @@ __device__ __forceinline__ void xfull_store4(float *xfull, int64_t off, float4 v
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int f32_exponent(float x) { return (int)((__float_as_uint(x) >> 23) & 0xFFu) - 127; }
 
-#ifndef H2_BM_PACK_SLAB
-#define H2_BM_PACK_SLAB 128
-#endif
-constexpr int kPackSlab = H2_BM_PACK_SLAB;     // features per work item of bm_pack_i8_kernel (64 / 128)
-static_assert(kPackSlab == 64 || kPackSlab == 128, "slab = 1 or 2 groups of 64 features, 2 or 4 of 32");
+constexpr int kPackSlab = 128;     // features per work item of bm_pack_i8_kernel (measured r02: 64-feature items make the
+                                   // kernel 11.4 instead of 13.6 us, -2 us on the cold round, nothing on the pipelined rate; not adopted)
 constexpr int kPackThreads = 256;
 
 struct I8Header {                  // first kI8HeaderBytes of the packed operand
