@@ -36,9 +36,14 @@ namespace h2 {
 
 constexpr int kPairGroups = 2;                              // producer groups of 4 warps per CTA
 constexpr int kPairThreads = (4 * kPairGroups + 2) * 32;    // 320
-// register cap: 320 x 144 + 256 x 64 (one CSR-gather CTA of the same round) <= 64 K registers per SM, so that the hop-1
-// gather can share the SM with the persistent MMA CTA
-constexpr int kPairMaxRegs = 144;
+// register cap of the persistent pair CTA: what it leaves of the SM's 64 K registers is what the CSR-gather CTAs of the same
+// round and the pack CTAs of the next one can use while it runs.  Measured (r02, pipelined round at the north-star point,
+// tools/pipeline_parts.py): 144 registers 48.1 us, 128: 46.1 us, 112: 46.3, 104: 46.6, 96 (spills): 47.9; no spills down to
+// 112.  (Gather CTAs of 4 instead of 8 warps: 46.0-47.0 us, not adopted.)
+#ifndef H2_BM_PAIR_MAXREGS
+#define H2_BM_PAIR_MAXREGS 128
+#endif
+constexpr int kPairMaxRegs = H2_BM_PAIR_MAXREGS;
 #ifdef H2_BM_PAIR_SEG_UNITS
 constexpr int kPairMaxSegUnits = H2_BM_PAIR_SEG_UNITS;      // test builds: force many accumulator cuts on small graphs
 #else

@@ -10,7 +10,10 @@
 
 namespace h2 {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef H2_GATHER_WARPS
+#define H2_GATHER_WARPS 8
+#endif
+constexpr int kWarpsPerCta = H2_GATHER_WARPS;   // CSR gather kernel: warps (= rows) per CTA
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr int kNumSms = 148;  // B200: 2 dies x 74 SMs
 

@@ -225,7 +225,7 @@ __device__ __forceinline__ float4 epilogue(float4 a, float scale, const float *b
 }
 
 template <int LPR, int NV, bool XB>
-__global__ void __launch_bounds__(kCtaThreads, NV == 1 ? 4 : (NV == 2 ? 3 : 2))
+__global__ void __launch_bounds__(kCtaThreads, (NV == 1 ? 1024 : (NV == 2 ? 768 : 512)) / kCtaThreads)
 fused_hops_gather_kernel(const __grid_constant__ RoundParams p) {
     extern __shared__ float4 s_part[];  // [kWarpsPerCta][d4] partial rows of a CTA-row
     const int lane = threadIdx.x & 31;
