@@ -2,7 +2,7 @@
 # traces of the pair kernel under several schedule settings (library built with H2_BM_TRACE), then per-part times
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=${1:-r02f}
+T=${1:-sweep}
 H2_BM_TRACE=1 python -m h2gcn_b200.build --force > /dev/null 2>&1
 i=0
 for c in ${COSTS:-"8,12,6"}; do
