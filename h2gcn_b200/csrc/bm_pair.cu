@@ -63,7 +63,7 @@ struct BmPairFix {        // one split (tile, group) item: Y rows = scale * sum 
     int32_t tile, group, slot_begin, n_slots;
 };
 
-template <int S, int FH>
+template <int S, int FH, bool SAFE = false>
 struct PairCfg {
     static constexpr int NBH = S * FH;                      // B rows in ONE CTA's shared memory per unit
     static constexpr int N = 2 * NBH;                       // accumulator columns: 128 / 192 / 256 / 384
@@ -77,8 +77,12 @@ struct PairCfg {
     // 34 KB CTAs of the NEXT round's pack kernel and the gather CTAs can share the SM (with a 224 KB ring the pipelined
     // rounds of bench.py ran 62 us apart instead of ~57: nothing else fitted next to the MMA CTA; the depth itself
     // made no difference between 9 and 13 stages, profiles/README.md r02b)
-    static constexpr int kBStgFit = (int)((176 * 1024 - 1024 - 8 * 32 * 36 * 4) / (kBStride + 1024));
-    static constexpr int kBStg = kBStgFit > 12 ? 12 : kBStgFit;
+    // SAFE launches (operands streaming from DRAM, release fence on the hand-over) are latency-bound on the B ring — every
+    // stage is held ~2.5 k cycles longer — and have little to gain from co-resident CTAs: they take the whole 227 KB
+    // (13 stages for 3 digits x 64 features instead of 9).
+    static constexpr int kBudgetKB = SAFE ? 225 : 176;
+    static constexpr int kBStgFit = (int)((kBudgetKB * 1024 - 1024 - 8 * 32 * 36 * 4) / (kBStride + 1024));
+    static constexpr int kBStg = kBStgFit > (SAFE ? 16 : 12) ? (SAFE ? 16 : 12) : kBStgFit;
     static constexpr int kStageStride = 36;                 // floats per staged row: 32 + 4 (16-byte aligned, bank spread)
     static constexpr size_t kSmem = (size_t)kBStg * (kBStride + kBitsBytes) + 8 * 32 * kStageStride * 4 + 1024;
     static_assert(kACol0 + kAStg * 16 <= 512 && N % 16 == 0, "TMEM budget / UMMA N");
@@ -151,7 +155,7 @@ __device__ __forceinline__ void red_release_gpu_add(int32_t *p, int v) {
 // instantiation keeps the per-unit arrive of the L2-resident regime free of the batching bookkeeping
 template <int S, int FH, bool SAFE>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kPairMaxRegs) bm_pair_kernel(const __grid_constant__ BmPairParams p) {
-    using Cfg = PairCfg<S, FH>;
+    using Cfg = PairCfg<S, FH, SAFE>;
     constexpr int NBH = Cfg::NBH, N = Cfg::N;
     constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride, kBitsBytes = Cfg::kBitsBytes;
     constexpr uint32_t kACol0 = Cfg::kACol0, kTmemCols = 512;
@@ -856,7 +860,7 @@ size_t pair_partial_bytes(int n_slots, int fh) { return (size_t)n_slots * kTileR
 
 template <int S, int FH, bool SAFE>
 static int pair_launch_ts(int n_pairs, const BmPairParams &p, cudaStream_t st) {
-    using Cfg = PairCfg<S, FH>;
+    using Cfg = PairCfg<S, FH, SAFE>;
     auto kern = bm_pair_kernel<S, FH, SAFE>;
     static bool attr_done[64] = {};
     int dev = 0;
