@@ -68,6 +68,11 @@ def _worker(rank, world, port, ret):
         x_full = torch.empty(n, d)
         all_gather_rows(torch.from_numpy(x[b:e].copy()), x_full, bounds)
         assert np.array_equal(x_full.numpy(), x)
+        # the same exchange with bf16 feature rows (BASELINE config 5): a pure copy, bit-identical on every rank
+        xb = torch.from_numpy(x).to(torch.bfloat16)
+        xb_full = torch.empty(n, d, dtype=torch.bfloat16)
+        all_gather_rows(xb[b:e].contiguous(), xb_full, bounds)
+        assert torch.equal(xb_full, xb)
         # shard-local round == the same rows of the single-process round (bit-exact: per-row order is P-independent)
         p2 = sp.csr_matrix((np.ones(len(col2)), col2, rp2), shape=(n, n))
         a1, a2 = O.sym_normalize(adj)[0], O.sym_normalize(p2)[0]
