@@ -180,14 +180,24 @@ __device__ __forceinline__ void accumulate_segment(const int32_t *__restrict__ c
     col += s;
     if (val) val += s;
     const int n = (int)(e - s);
-    for (int base = 0; base < n; base += 32) {
+    // the (col, val) pairs of batch b + 1 are loaded BEFORE the gathers of batch b are issued: their latency (two dependent
+    // loads in factored mode) hides behind the batch instead of opening every batch with an exposed round trip
+    auto load_cv = [&](int base, int &c, float &v) {
         const int k = base + lane;
-        int c = 0;
-        float v = 0.f;
+        c = 0;
+        v = 0.f;
         if (k < n) {
             c = __ldg(col + k);
             v = val ? __ldg(val + k) : __ldg(dinv + c);
         }
+    };
+    int c;
+    float v;
+    load_cv(0, c, v);
+    for (int base = 0; base < n; base += 32) {
+        int cn = 0;
+        float vn = 0.f;
+        if (base + 32 < n) load_cv(base + 32, cn, vn);
         if (n - base >= 32) {
 #pragma unroll
             for (int t = 0; t < 32; t += G * U) gather_step<LPR, NV, U, XB, true>(t, 32, c, v, xlane, row_bytes, qoff, grp, acc);
@@ -195,6 +205,8 @@ __device__ __forceinline__ void accumulate_segment(const int32_t *__restrict__ c
             const int cnt = n - base;
             for (int t = 0; t < cnt; t += G * U) gather_step<LPR, NV, U, XB, false>(t, cnt, c, v, xlane, row_bytes, qoff, grp, acc);
         }
+        c = cn;
+        v = vn;
     }
 }
 
