@@ -80,7 +80,10 @@ struct PairCfg {
     // SAFE launches (operands streaming from DRAM, release fence on the hand-over) are latency-bound on the B ring — every
     // stage is held ~2.5 k cycles longer — and have little to gain from co-resident CTAs: they take the whole 227 KB
     // (13 stages for 3 digits x 64 features instead of 9).
-    static constexpr int kBudgetKB = SAFE ? 225 : 176;
+#ifndef H2_BM_PAIR_SMEM_KB
+#define H2_BM_PAIR_SMEM_KB 176
+#endif
+    static constexpr int kBudgetKB = SAFE ? 225 : H2_BM_PAIR_SMEM_KB;
     static constexpr int kBStgFit = (int)((kBudgetKB * 1024 - 1024 - 8 * 32 * 36 * 4) / (kBStride + 1024));
     static constexpr int kBStg = kBStgFit > (SAFE ? 16 : 12) ? (SAFE ? 16 : 12) : kBStgFit;
     static constexpr int kStageStride = 36;                 // floats per staged row: 32 + 4 (16-byte aligned, bank spread)
