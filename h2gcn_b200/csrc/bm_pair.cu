@@ -12,21 +12,29 @@
 //    FH-feature half — byte for byte the tile bm_pack_i8_kernel writes), so the L2 -> SM operand traffic per row is that
 //    of a 512-row tile.
 //  * Split tiles are finished IN the kernel: stream-K ranges cut a (tile, group) item into segments; every segment of
-//    a split item converts its int32 accumulators to ONE fp32 value per feature and parks it in a partial slot, then
-//    bumps the item's arrival counter (one per CTA rank: the two CTAs own disjoint row halves).  The CTA that arrives
-//    LAST adds the item's slots in ascending order (deterministic whoever does it), scales and writes Y for its 128 rows.
-//    Nobody ever waits: no fix-up launch, no co-residency assumption, and SMs are released as soon as their range is
-//    done, which is what the pipelined rounds of bench.py need.  (Measured alternatives, profiles/README.md r02b: fixed
-//    sender / receiver roles put two epilogues in series behind the slowest CTA — 77 k cycles against 46-49 k for
-//    CTAs without a receiver segment; a grid barrier followed by an even split of the rows made every CTA hold its SM
-//    for 10-16 k idle cycles — better latency, 62 instead of 57 us per pipelined round.)
+//    a split item converts its int32 accumulators to ONE fp32 value per feature.  The segment the schedule expects to
+//    end last (always the last one of its pair) is the item's DESIGNATED finisher: it drains all its accumulator blocks
+//    (the second one into the B ring, free by then), waits — bounded — for the arrival counter of its CTA rank, adds the
+//    other segments' slots to its staged values in slot order inside its own write-out and stores Y.  The other segments
+//    park their values in a partial slot and bump the counter; if the finisher's patience runs out it does the same and
+//    whoever arrives LAST adds the slots in ascending order.  Either way the sum is deterministic, nobody waits for
+//    long, there is no fix-up launch and no co-residency assumption.  (Measured alternatives, profiles/README.md r02:
+//    fixed sender / receiver roles without a time bound: 77 k cycles against 46-49 k; a grid barrier and an even split of
+//    the rows: 10-16 k idle cycles per CTA; last-arriver only: the sum sat on the critical path of the pair that ended
+//    last, 60 k against 55 k cycles for the slowest CTA.)
+//  * The ranges are cut at equal COST (units + calibrated epilogue costs), not equal unit counts (pair_schedule), and the
+//    producers stage the first units of the NEXT segment before they drain the accumulators of the current one.
 //  * Segments are also cut every 2048 units (2^17 columns): |sum| <= 2^17 * 64 * 128 = 2^30 keeps the int32 accumulators
 //    exact for any number of columns (the single-CTA kernel refuses n_cols > 2^17).
+//  * Hand-overs between the two CTAs (bm_common.cuh): the accumulator hand-over of the peer is relayed by its idle warp 9
+//    with a cluster-scope release; the operand hand-over carries a release fence per 4 units in launches whose operands
+//    stream from DRAM (template SAFE, chosen per launch from the operand bytes) and is a plain arrive otherwise.
 //
 // Roles per CTA (10 warps): warps 0..7 = A producers (two groups of 4 on alternate units; thread = bitmap row: 16
 // rotate+mask words -> `tcgen05.st` -> wait::st -> remote arrive on the leader's barrier), then epilogue; warp 8 = TMA
 // (`cp.async.bulk`: B half + expansion constants + 1 KB of bitmap per unit); warp 9 = TMEM allocation and, in the
-// leader CTA, the ONE thread that issues every MMA / commit for both CTAs.
+// leader CTA, the ONE thread that issues every MMA / commit for both CTAs — in the peer CTA, the relay of the
+// accumulator hand-over.
 #include <stdint.h>
 #include <stdlib.h>
 
