@@ -12,8 +12,11 @@
 // run to run and independent of how rows are sharded over GPUs.
 //
 // Inner loop: a warp loads 32 (col, val) pairs coalesced, then walks them with warp shuffles; every X row is
-// fetched with 128-bit read-only loads (`ld.global.nc.v4`), 8 rows in flight per warp.  When d/4 < 32 the warp is
-// split into 32/LPR groups that take different nonzeros and are combined with a butterfly at the end.
+// fetched with 128-bit read-only loads (`ld.global.nc.v4`), 8 rows in flight per warp, and the next batch's pairs are
+// loaded before the current batch's gathers are issued.  When d/4 < 32 the warp is split into 32/LPR groups that take
+// different nonzeros and are combined with a butterfly at the end.  The row type (fp32 / bf16) is a template parameter
+// and full batches are unpredicated: 8 issued instructions per stored entry (r02; 48 before, issue-bound), which puts the
+// kernel on the L2 -> SM roofline for long rows (82.6 % `lts__throughput` on the all-CSR round, profiles/README.md r02).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
