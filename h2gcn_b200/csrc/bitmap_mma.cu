@@ -29,15 +29,14 @@
 // that does not cover a whole (row tile, group) writes an fp32 partial tile and `bm_fixup_kernel` adds the partials
 // of a tile in ascending slot order (deterministic).  Measurements behind these choices: profiles/README.md.
 //
-// Arithmetics (`splits`, include/h2gcn_b200.h).  The description above is the bf16 one (kind::f16, 2 / 3 pieces of X').
-// The DEFAULT is int8 (`I8 = true`, H2_SPLITS_I8X2 / I8X3): X' as block-fixed-point — one step for the matrix, a block
-// exponent 2^t (t in 0..6) per ROW of X' carried by the 0/1 operand as bytes 0 / 2^t, 2 / 3 balanced base-256 digits as
-// the int8 B operand — on `tcgen05.mma kind::i8` (K = 32, twice the bf16 MAC rate, EXACT int32 accumulation; the
-// epilogue converts and scales once).  Differences: bm_absmax_kernel + bm_pack_i8_kernel build the operand (B tiles of
-// [S*DG x 64] bytes, SWIZZLE_64B, + 128 bytes of per-word {rotate, mask} constants); bitmaps in bit order 1 so that
-// an operand word is one rotate + one mask; A stages of 2 x 16 TMEM columns (8 of them); the 8 producer warps form
-// two groups of 4 that take alternate units and expand two rows per thread.  `bm_mma_pair_kernel` (opt-in) is the
-// `cta_group::2` form of the same product.
+// Arithmetics (`splits`, include/h2gcn_b200.h).  The kernel in THIS file (bm_mma_kernel, single CTA, kind::f16) serves the
+// 2 / 3 bf16-piece arithmetics.  The DEFAULT is int8 (H2_SPLITS_I8X3 / I8X2): X' as block-fixed-point — one step for the
+// matrix, an exponent 2^t (t in 0..6) per ROW of X' carried by the 0/1 operand as bytes 0 / 2^t, 3 / 2 balanced base-256
+// digits as the int8 B operand — on `tcgen05.mma.cta_group::2.kind::i8` (K = 32, twice the bf16 MAC rate, EXACT int32
+// accumulation; the epilogue converts and scales once): bm_pair_kernel in bm_pair.cu.  This file also holds what both
+// share: the tile-bitmap format and its construction, the stream-K schedules, and the operand packing — bm_pack_kernel
+// (bf16 pieces) and the cooperative bm_pack_i8_kernel (B tiles of [S*DG x 64] bytes, SWIZZLE_64B, + 128 bytes of per-word
+// {rotate, mask} constants; bitmaps in bit order 1 so that an operand word is one rotate + one mask).
 #include "bm_common.cuh"
 
 namespace h2 {
@@ -424,26 +423,26 @@ struct BmParams {
     int32_t n_rows, d, n_groups, splits;
 };
 
-// I8 = false: bf16 pieces (kind::f16, K = 16, A stage = 2 x 32 TMEM columns, B tile rows of 128 bytes, SWIZZLE_128B)
-// I8 = true : int8 digits (kind::i8, K = 32, A stage = 2 x 16 TMEM columns, B tile rows of 64 bytes, SWIZZLE_64B,
-//             followed by the chunk's 16 {rotate, mask} pairs); same warp roles, barriers and schedule.
-template <int DG, int S, bool I8>
+// bf16 pieces: kind::f16, K = 16, A stage = 2 x 32 TMEM columns, B tile rows of 128 bytes, SWIZZLE_128B.  (Round 1 also
+// instantiated this kernel for the int8 digits; since r02 every int8 round runs on bm_pair_kernel, bm_pair.cu, and the
+// int8 branches were removed here.)
+template <int DG, int S>
 struct BmCfg {
     static constexpr int NB = S * DG;                                             // UMMA N
-    static constexpr uint32_t kBBytes = I8 ? NB * 64 + kI8ConstBytes : NB * 128;   // bytes per B tile in global memory
+    static constexpr uint32_t kBBytes = NB * 128;                                 // bytes per B tile in global memory
     static constexpr uint32_t kBStride = (kBBytes + 1023u) & ~1023u;              // shared-memory stage stride
     static constexpr uint32_t kAccCols = 2 * NB;                                  // two 128-row halves
-    static constexpr uint32_t kAHalfCols = I8 ? 16 : 32;                          // TMEM columns of one half of an A stage
-    static constexpr int kAStg = I8 ? ((512 - (int)kAccCols) / 32 >= 8 ? 8 : 4) : kAStages;
+    static constexpr uint32_t kAHalfCols = 32;                                    // TMEM columns of one half of an A stage
+    static constexpr int kAStg = kAStages;
     static constexpr size_t kSmem = (size_t)kBStages * (kBStride + kTileRows * 8) + 8 * 32 * (DG + 4) * 4 + 1024;
     static_assert(kAccCols + kAStg * 2 * kAHalfCols <= 512 && NB % 16 == 0 && NB >= 16 && NB <= 256, "UMMA N / TMEM budget");
     static_assert(kAStg <= kAStagesMax && 8 % kAStg == 0, "A stage ring");
 };
 
-template <int DG, int S, bool I8>
-__global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
-    using Cfg = BmCfg<DG, S, I8>;
-    constexpr int kProducerSets = bm_producer_sets(I8);
+template <int DG, int S>
+__global__ void __launch_bounds__(bm_threads(false), 1) bm_mma_kernel(const __grid_constant__ BmParams p) {
+    using Cfg = BmCfg<DG, S>;
+    constexpr int kProducerSets = bm_producer_sets(false);
     constexpr int NB = Cfg::NB;
     constexpr uint32_t kBBytes = Cfg::kBBytes, kBStride = Cfg::kBStride;
     constexpr uint32_t kAccCols = Cfg::kAccCols;
@@ -452,7 +451,7 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
     constexpr int kAStg = Cfg::kAStg;
     constexpr uint32_t kTmemCols = 512;
     // instruction descriptor: D format (fp32 = 1 / int32 = 2) | A, B format (bf16 = 1 / signed int8 = 1) | N >> 3 | M >> 4
-    constexpr uint32_t kIdesc = ((I8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Shared-window addresses are made opaque to the compiler: left alone it REMATERIALISES them inside the unit loops
@@ -487,7 +486,7 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
     if (threadIdx.x == 0) {
         BM_TRACE(0);
         for (int s = 0; s < kAStg; ++s) {
-            mbar_init(bar_full_a + 8 * s, I8 ? 4 : 8);    // one arrive per A-producer warp of the unit
+            mbar_init(bar_full_a + 8 * s, 8);             // one arrive per A-producer warp of the unit
             mbar_init(bar_empty_a + 8 * s, 1);   // tcgen05.commit
         }
         for (int s = 0; s < kBStages; ++s) {
@@ -565,14 +564,9 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                    for (int k = 0; k < kChunkCols / (I8 ? 32 : 16); ++k) {   // 32 operand bytes (8 TMEM columns) per step
-                        if constexpr (I8)
-                            umma_i8_ts(tmem_base + half * NB, a0 + half * kAHalfCols + k * 8, umma_desc_sw64(b0 + k * 32), kIdesc,
-                                       k > 0 ? 1u : acc_first);
-                        else
-                            umma_bf16_ts(tmem_base + half * NB, a0 + half * kAHalfCols + k * 8, umma_desc_sw128(b0 + k * 32), kIdesc,
-                                         k > 0 ? 1u : acc_first);
-                    }
+                    for (int k = 0; k < kChunkCols / 16; ++k)   // 32 operand bytes (8 TMEM columns) per step
+                        umma_bf16_ts(tmem_base + half * NB, a0 + half * kAHalfCols + k * 8, umma_desc_sw128(b0 + k * 32), kIdesc,
+                                     k > 0 ? 1u : acc_first);
                 }
                 umma_commit(bar_empty_a + 8 * sa);   // both arrive once the MMAs above have consumed their operands
                 umma_commit(bar_empty_b + 8 * sb);
@@ -626,44 +620,19 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
             for (int once = 0; once < 1; ++once, ++acc_it) {
                 bool pending = false;
                 uint32_t pending_sa = 0;
-                // bf16: sets of 8 warps (half x quarter) take alternate units.  int8: a unit is only 256 cycles of MMA work
-                // while one warp needs several hundred cycles per unit it expands (a single warp issues one dependent
-                // instruction every ~4.5 cycles, and the phase check of an mbarrier completed by TMA costs ~200), so the
-                // warps are grouped by 4 (one per TMEM lane quarter), group k takes the units with it % kStep == k, a
-                // thread expands BOTH of its rows (lane of half 0 and of half 1: the unit's {rotate, mask} constants are
-                // loaded once for two rows), and the phase check of the group's next unit is started one unit ahead.
-                constexpr int kStep = I8 ? 2 * kProducerSets : kProducerSets;
-                const int mine = I8 ? (pw >> 2) : set;
+                // sets of 8 warps (half x quarter) take alternate units
+                constexpr int kStep = kProducerSets;
+                const int mine = set;
                 const int skip = (int)((uint32_t)(mine + kStep - (int)(it % kStep)) % kStep);
                 const uint32_t it_end = it + (uint32_t)(sg.unit_end - sg.unit_begin);
                 it += skip;
-                uint32_t ready = 0;
-                if (I8 && sg.unit_begin + skip < sg.unit_end) ready = mbar_try_wait(bar_full_b + 8 * (it % kBStages), (it / kBStages) & 1);
                 // one unit: expand the bitmap row(s) into `a`, publish the previous unit, wait for a free A stage, store
                 auto produce = [&](int u, uint32_t (&a)[32]) {
                     const uint32_t sb = it % kBStages, pb = (it / kBStages) & 1;
                     // the unit's bitmap rides in the B stage (TMA-prefetched)
-                    if (!I8 || !ready) { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(0); }
+                    { BM_WAIT_BEGIN(); mbar_wait(bar_full_b + 8 * sb, pb); BM_WAIT_END(0); }
                     if ((warp & 3) == 0 && lane == 0) BM_T2(1, it);
-                    if constexpr (I8) {
-                        // word j = columns 4j..4j+3 as bytes 0 / 2^t(column): i8_expand_word; {rotate, mask} per word
-                        // ride behind the B tile (the exponents t belong to the chunk's rows of X').
-                        const uint4 *cst = reinterpret_cast<const uint4 *>(smem_raw + (smem_base - smem_raw_u32) + sb * kBStride + NB * 64);
-                        const unsigned long long b0 = bits_gen[sb * kTileRows + quarter * 32 + lane];
-                        const unsigned long long b1 = bits_gen[sb * kTileRows + 128 + quarter * 32 + lane];
-                        const uint32_t x0 = (uint32_t)b0, x1 = (uint32_t)(b0 >> 32), y0 = (uint32_t)b1, y1 = (uint32_t)(b1 >> 32);
-                        if (u + kStep < sg.unit_end)   // start the next unit's phase check behind the expansion below
-                            ready = mbar_try_wait(bar_full_b + 8 * ((it + kStep) % kBStages), ((it + kStep) / kBStages) & 1);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint4 c = cst[q];
-                            const uint32_t x = q < 4 ? x0 : x1, y = q < 4 ? y0 : y1;
-                            a[2 * q] = i8_expand_word(x, c.x, c.y);
-                            a[2 * q + 1] = i8_expand_word(x, c.z, c.w);
-                            a[16 + 2 * q] = i8_expand_word(y, c.x, c.y);       // half 1: the next 16 TMEM columns
-                            a[16 + 2 * q + 1] = i8_expand_word(y, c.z, c.w);
-                        }
-                    } else {
+                    {
                         const unsigned long long bits = bits_gen[sb * kTileRows + r];
                         // element k of the row -> bf16 2.0 (0x4000) or 0: word j = (bit 2j) << 14 | (bit 2j+1) << 30
 #pragma unroll
@@ -686,7 +655,7 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                     { BM_WAIT_BEGIN(); mbar_wait(bar_empty_a + 8 * sa, pa ^ 1); BM_WAIT_END(1); }
                     if ((warp & 3) == 0 && lane == 0) BM_T2(3, it);
                     tc_fence_after();
-                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * kAStageCols + (I8 ? 0 : half * kAHalfCols), a);
+                    cuda::ptx::tcgen05_st_32x32b(t_lane + kACol0 + sa * kAStageCols + half * kAHalfCols, a);
                     if ((warp & 3) == 0 && lane == 0) BM_T2(4, it);
                     pending = true;
                     pending_sa = sa;
@@ -711,8 +680,8 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                 if (warp == 0 && lane == 0) BM_TRACE(6 + 6 * w);
                 const int64_t grow = (int64_t)sg.tile * kTileRows + r;
                 const bool row_ok = grow < p.n_rows;
-                // bf16: A holds 2.0, not 1.0; int8: integer accumulators in units of the quantisation step
-                const float scale = (I8 ? __ldg(p.xstep) : 0.5f) * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
+                // A holds 2.0, not 1.0
+                const float scale = 0.5f * ((row_ok && p.dinv_row) ? p.dinv_row[grow] : 1.f);
                 const int valid_cols = sg.partial_slot < 0 ? min(DG, p.d - g * DG) : DG;
                 const uint32_t t_row = t_lane + half * NB;
                 // TMEM -> registers (lane = row) -> per-warp shared-memory stage; the accumulator is released as soon as
@@ -731,17 +700,9 @@ __global__ void __launch_bounds__(bm_threads(I8), 1) bm_mma_kernel(const __grid_
                         float *po = &o.x;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float v;
-                            if constexpr (I8) {   // digits, most significant first: sum_s 256^(S-1-s) * acc_s
-                                v = (float)(int32_t)acc[S - 1][q + e];
-                                float wgt = 256.f;
+                            float v = __uint_as_float(acc[S - 1][q + e]);
 #pragma unroll
-                                for (int s = S - 2; s >= 0; --s, wgt *= 256.f) v = fmaf((float)(int32_t)acc[s][q + e], wgt, v);
-                            } else {
-                                v = __uint_as_float(acc[S - 1][q + e]);
-#pragma unroll
-                                for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
-                            }
+                            for (int s = S - 2; s >= 0; --s) v += __uint_as_float(acc[s][q + e]);  // small pieces first
                             po[e] = v * scale;
                         }
                         *reinterpret_cast<float4 *>(stage + lane * kStageStride + c0 + q) = o;
@@ -1211,13 +1172,13 @@ static int bm_smem_once(K kern, size_t smem, bool *done) {
     return H2_OK;
 }
 
-template <int DG, int S, bool I8 = false>
+template <int DG, int S>
 static int bm_launch(const BmSched &sc, const char *base, const BmParams &p, cudaStream_t st) {
-    constexpr size_t smem = BmCfg<DG, S, I8>::kSmem;
-    auto kern = bm_mma_kernel<DG, S, I8>;
+    constexpr size_t smem = BmCfg<DG, S>::kSmem;
+    auto kern = bm_mma_kernel<DG, S>;
     static bool attr_done[64] = {};
     { int rc = bm_smem_once(kern, smem, attr_done); if (rc != H2_OK) return rc; }
-    kern<<<sc.n_ctas, bm_threads(I8), smem, st>>>(p);
+    kern<<<sc.n_ctas, bm_threads(false), smem, st>>>(p);
     H2_LAUNCHED("bm_mma_kernel");
     if (sc.n_fix > 0) {
         bm_fixup_kernel<DG><<<dim3((kTileRows * DG / 4 + 255) / 256, sc.n_fix), 256, 0, st>>>((const BmFix *)(base + sc.off_fix), p.n_rows, p.d, p.partial, p.Y, p.ldy);
