@@ -20,15 +20,12 @@ constexpr int kTileRows = 256;   // two UMMA M=128 accumulators share every B ti
 constexpr int kChunkCols = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kAStages = 4;    // A tiles live in TMEM: 4 x (2 halves x 32 columns) next to 2 x 128 accumulator columns
 constexpr int kBStages = 8;    // B tiles (<= 16 KB) + unit bitmaps (2 KB) in shared memory
-// sets of 8 A-producer/epilogue warps: 1 for the bf16 kernel (keeps the register footprint small enough for a CSR-gather
-// CTA of the same round to share the SM), 2 for the int8 kernel (a unit is half the MMA time: see the producer loop)
-#ifndef H2_BM_I8_SETS
-#define H2_BM_I8_SETS 1
-#endif
-__host__ __device__ constexpr int bm_producer_sets(bool i8) { return i8 ? H2_BM_I8_SETS : 1; }
-__host__ __device__ constexpr int bm_threads(bool i8) { return (8 * bm_producer_sets(i8) + 2) * 32; }   // producers, TMA warp, MMA warp (last)
+// single-CTA (bf16-piece) kernel: ONE set of 8 A-producer / epilogue warps (keeps the register footprint small enough for a
+// CSR-gather CTA of the same round to share the SM) + TMA warp + MMA warp (last)
+__host__ __device__ constexpr int bm_producer_sets(bool) { return 1; }
+__host__ __device__ constexpr int bm_threads(bool) { return (8 * 1 + 2) * 32; }
 constexpr uint32_t kBmMagic = 0x48324234u;  // "H2B4"
-constexpr int kAStagesMax = 8;   // int8 A tiles are half as wide: up to 8 stages of 32 TMEM columns
+constexpr int kAStagesMax = 8;
 
 // `splits` codes (include/h2gcn_b200.h): 2 / 3 = bf16 pieces; H2_SPLITS_I8X2 / H2_SPLITS_I8X3 = int8 digits with
 // per-4-row block exponents (kind::i8, exact int32 accumulation)
@@ -161,16 +158,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same for int8 operands (K = 32 per instruction), exact int32 accumulation
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, SWIZZLE_64B operand tile: rows of 64 bytes, 8-row atoms of 512 bytes (verified with tools/umma_i8_probe.cu)
