@@ -657,6 +657,16 @@ def main_single(args):
                 ref = cbind.fused_round(hh[0][0], hh[0][1], hh[0][2], hh[1][0], hh[1][1], hh[1][2], x_host_check, threads=host_threads())
             other[name]["parity"] = parity_metrics(yy, ref)
         line["config"]["parity"] = par
+        # repeatability of the timed path: the same round 200 more times into a scratch output, compared BIT for BIT with
+        # the output the parity above was computed on (the tensor-core hop's cross-CTA hand-over)
+        y_rep = torch.empty_like(ys[0])
+        y_first = torch.from_numpy(np.ascontiguousarray(y_head)).to(dev)
+        same = 0
+        for _ in range(200):
+            y_rep.fill_(float("nan"))
+            graphs[0].round(xs[0], y_rep, [0, d])
+            same += int(torch.equal(y_rep, y_first))
+        par["bitwise_repeatable_launches"] = f"{same} of 200"
     _JSON_OUT.write(json.dumps(line) + "\n")
     _JSON_OUT.flush()
 
